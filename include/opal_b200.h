@@ -1,0 +1,66 @@
+/*
+ * opal_b200.h -- extended C ABI of libopal_b200.so (beneath the drop-in opal.h).
+ *
+ * opal.h's opalSearchDatabase packs and uploads the database on every call, as the reference's
+ * signature demands (reference src/opal.h:150-154 takes host pointers each time).  Real workloads
+ * run many queries against one database, so the same engine is also reachable through a
+ * resident-database handle: pack + upload once, search many times.  Plain pointers and sizes
+ * only; every function is safe to bind from C, ctypes, cgo, JNI ...
+ *
+ * Scores / end locations returned here are in CALLER order (index i <-> db[i]), -1 for unset.
+ */
+#ifndef OPAL_B200_H
+#define OPAL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OpalB200Db OpalB200Db;
+
+/* Number of CUDA devices this process can use (0 => every search returns OPAL_ERR_NO_SIMD_SUPPORT). */
+int opalb200_device_count(void);
+
+/* Text of the last CUDA / argument error seen by the calling thread ("" if none). */
+const char* opalb200_last_error(void);
+
+/*
+ * Length-sorts the database (longest first), concatenates it in that order and uploads it to
+ * `device`'s HBM.  Same db / dbLength / dbSeqLengths meaning as opalSearchDatabase
+ * (reference src/opal.h:107-109).  Returns NULL on failure.
+ */
+OpalB200Db* opalb200_db_create(unsigned char* db[], int dbLength, const int dbSeqLengths[], int device);
+void opalb200_db_destroy(OpalB200Db* handle);
+
+/* Sequences / residues held by the handle. */
+int opalb200_db_length(const OpalB200Db* handle);
+long long opalb200_db_residues(const OpalB200Db* handle);
+
+/*
+ * Score (searchType 0) or score + end location (searchType 1) of `query` against every database
+ * sequence whose skip[i] is 0 (skip may be NULL).  Arguments as opalSearchDatabase.  Outputs are
+ * arrays of dbLength ints in caller order; endQuery/endTarget may be NULL for searchType 0.
+ * deviceMs (nullable) receives the CUDA-event time from the first kernel launch to the last kernel
+ * end of this search -- the window the reference times around its call (src/opal_aligner.cpp:157-165).
+ * Returns 0 or an OPAL_ERR_* code.
+ */
+int opalb200_db_search(OpalB200Db* handle, const unsigned char query[], int queryLength,
+                       int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength,
+                       int searchType, int mode, const unsigned char* skip,
+                       int* scores, int* endQuery, int* endTarget, float* deviceMs);
+
+/* Statistics of the last search on this handle: kernels launched, targets re-run in 32 bits. */
+void opalb200_db_last_stats(const OpalB200Db* handle, int* kernelLaunches, int* rerun32, int* G, int* R, int* passes);
+
+/*
+ * Measures the packed-DPX issue rate of `device` with a register-only kernel running the SW cell
+ * recurrence (6 s16x2 instructions per 2 cells): returns giga cell updates per second that the
+ * integer pipe can sustain (the roofline of SURVEY.md section 8d), and through the out-params the
+ * thread-instructions/s and the kernel time.
+ */
+double opalb200_measure_dpx_peak(int device, double* threadInstrPerSec, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPAL_B200_H */

@@ -1,0 +1,11 @@
+// align.h -- the OPAL_SEARCH_ALIGNMENT stage (start location + operation string).
+#pragma once
+#include "../../include/opal.h"
+#include "engine.h"
+
+namespace opalb200 {
+// For every database entry: derive start location and alignment from its (score, end location),
+// as reference src/opal.cpp:1475-1507 does with findAlignment (:1236-1431).
+int align_database(DeviceDb* ddb, const unsigned char* query, int Q, unsigned char* const* db, int n, const int* lens,
+                   int Go, int Ge, const int* matrix, int A, OpalSearchResult* results[], int mode);
+}  // namespace opalb200

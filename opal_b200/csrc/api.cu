@@ -1,0 +1,169 @@
+// api.cu -- the C ABI of libopal_b200.so: opal.h (drop-in) and opal_b200.h (resident handle).
+//
+// opalSearchDatabase mirrors reference src/opal.cpp:1435-1519 step by step -- skip mask from
+// prefilled records, score/end search, early return on error, then either the alignment stage
+// or the "no alignment" field fill -- with the SIMD passes replaced by DeviceDb::search.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/opal.h"
+#include "../../include/opal_b200.h"
+#include "align.h"
+#include "engine.h"
+
+using namespace opalb200;
+
+static int default_device() {
+    const char* e = getenv("OPAL_B200_DEVICE");
+    return e ? atoi(e) : 0;
+}
+
+extern "C" {
+
+void opalInitSearchResult(OpalSearchResult* r) {  // reference src/opal.cpp:1549-1555
+    r->scoreSet = 0;
+    r->startLocationTarget = r->startLocationQuery = -1;
+    r->endLocationTarget = r->endLocationQuery = -1;
+    r->alignment = NULL;
+    r->alignmentLength = 0;
+}
+
+int opalSearchResultIsEmpty(const OpalSearchResult r) { return !r.scoreSet; }  // :1557-1559
+
+void opalSearchResultSetScore(OpalSearchResult* r, int score) {  // :1561-1564
+    r->scoreSet = 1;
+    r->score = score;
+}
+
+int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db[], int dbLength, int dbSeqLengths[],
+                       int gapOpen, int gapExt, int* scoreMatrix, int alphabetLength, OpalSearchResult* results[],
+                       const int searchType, int mode, int overflowMethod) {
+    (void)overflowMethod;  // OPAL_OVERFLOW_SIMPLE / _BUCKETS only schedule the reference's passes; results are equal
+    if (mode != OPAL_MODE_NW && mode != OPAL_MODE_HW && mode != OPAL_MODE_OV && mode != OPAL_MODE_SW)
+        return OPAL_ERR_INVALID_MODE;  // :1469-1473, results untouched
+    if (dbLength <= 0) return 0;
+
+    // Entries that already hold what this search level needs are not recomputed (:1446-1451).
+    std::vector<unsigned char> skip(dbLength);
+    bool anyWork = false;
+    for (int i = 0; i < dbLength; i++) {
+        const OpalSearchResult* r = results[i];
+        skip[i] = r->scoreSet && (searchType == OPAL_SEARCH_SCORE || (r->endLocationQuery >= 0 && r->endLocationTarget >= 0));
+        anyWork |= !skip[i];
+    }
+    const int wantEnd = searchType != OPAL_SEARCH_SCORE;
+    DeviceDb* ddb = nullptr;
+    if (anyWork || searchType == OPAL_SEARCH_ALIGNMENT) {
+        ddb = DeviceDb::create(db, dbLength, dbSeqLengths, default_device());
+        if (!ddb) return OPAL_ERR_NO_SIMD_SUPPORT;
+    }
+    int status = 0;
+    if (anyWork) {
+        std::vector<int> sc(dbLength), eq(dbLength, -1), et(dbLength, -1);
+        status = ddb->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd, mode, skip.data(),
+                             sc.data(), eq.data(), et.data(), nullptr);
+        if (status == 0) {
+            for (int i = 0; i < dbLength; i++) {
+                if (skip[i]) continue;
+                opalSearchResultSetScore(results[i], sc[i]);
+                results[i]->endLocationQuery = wantEnd ? eq[i] : -1;  // :420-426, 869-905
+                results[i]->endLocationTarget = wantEnd ? et[i] : -1;
+            }
+        }
+    }
+    if (status == 0 && searchType == OPAL_SEARCH_ALIGNMENT)
+        status = align_database(ddb, query, queryLength, db, dbLength, dbSeqLengths, gapOpen, gapExt, scoreMatrix, alphabetLength,
+                                results, mode);
+    delete ddb;
+    if (status) return status;  // :1473
+    if (searchType != OPAL_SEARCH_ALIGNMENT) {  // :1508-1515
+        for (int i = 0; i < dbLength; i++) {
+            results[i]->alignment = NULL;
+            results[i]->alignmentLength = -1;
+            results[i]->startLocationQuery = -1;
+            results[i]->startLocationTarget = -1;
+        }
+    }
+    return 0;
+}
+
+int opalSearchDatabaseRescore(unsigned char query[], int queryLength, unsigned char* db[], int dbLength, int dbSeqLengths[],
+                              int gapOpen, int gapExt, int* scoreMatrix, int alphabetLength, OpalSearchResult* results[],
+                              const int searchType, int mode, int overflowMethod) {
+    return opalSearchDatabase(query, queryLength, db, dbLength, dbSeqLengths, gapOpen, gapExt, scoreMatrix, alphabetLength,
+                              results, searchType, mode, overflowMethod);
+}
+
+int opalSearchDatabaseCharSW(unsigned char query[], int queryLength, unsigned char** db, int dbLength, int dbSeqLengths[],
+                             int gapOpen, int gapExt, int* scoreMatrix, int alphabetLength, OpalSearchResult* results[]) {
+    // reference src/opal.cpp:1522-1546: SW scores that fit 8 bits; the others come back unset (-1).
+    if (dbLength <= 0) return 0;
+    bool argsFit = !(gapOpen < -128 || 127 < gapOpen || gapExt < -128 || 127 < gapExt);  // :178-180
+    for (int i = 0; argsFit && i < alphabetLength * alphabetLength; i++)
+        if (scoreMatrix[i] < -128 || 127 < scoreMatrix[i]) argsFit = false;               // :188-193
+    std::vector<int> sc(dbLength, -1);
+    int rc = argsFit ? 0 : OPAL_ERR_OVERFLOW;
+    if (argsFit) {
+        DeviceDb* ddb = DeviceDb::create(db, dbLength, dbSeqLengths, default_device());
+        if (!ddb) return OPAL_ERR_NO_SIMD_SUPPORT;
+        const int st = ddb->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, 0, OPAL_MODE_SW, nullptr,
+                                   sc.data(), nullptr, nullptr, nullptr);
+        delete ddb;
+        if (st == OPAL_ERR_NO_SIMD_SUPPORT) return st;
+        if (st) std::fill(sc.begin(), sc.end(), -1);
+    }
+    for (int i = 0; i < dbLength; i++) {
+        if (argsFit && sc[i] >= 0 && sc[i] <= 127) {
+            opalSearchResultSetScore(results[i], sc[i]);
+            results[i]->endLocationQuery = results[i]->endLocationTarget = -1;  // :423-426
+        } else {
+            results[i]->score = -1;  // :1538-1541
+            results[i]->scoreSet = 0;
+            rc = OPAL_ERR_OVERFLOW;
+        }
+    }
+    return rc;
+}
+
+// ------------------------------------------------------------------ opal_b200.h
+int opalb200_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+const char* opalb200_last_error(void) { return last_error(); }
+
+OpalB200Db* opalb200_db_create(unsigned char* db[], int dbLength, const int dbSeqLengths[], int device) {
+    return reinterpret_cast<OpalB200Db*>(DeviceDb::create(db, dbLength, dbSeqLengths, device));
+}
+
+void opalb200_db_destroy(OpalB200Db* h) { delete reinterpret_cast<DeviceDb*>(h); }
+
+int opalb200_db_length(const OpalB200Db* h) { return reinterpret_cast<const DeviceDb*>(h)->size(); }
+
+long long opalb200_db_residues(const OpalB200Db* h) { return reinterpret_cast<const DeviceDb*>(h)->residues(); }
+
+int opalb200_db_search(OpalB200Db* h, const unsigned char query[], int queryLength, int gapOpen, int gapExt,
+                       const int* scoreMatrix, int alphabetLength, int searchType, int mode, const unsigned char* skip,
+                       int* scores, int* endQuery, int* endTarget, float* deviceMs) {
+    if (!h || !scores) return OPAL_ERR_NO_SIMD_SUPPORT;
+    const int wantEnd = searchType != OPAL_SEARCH_SCORE && endQuery && endTarget;
+    return reinterpret_cast<DeviceDb*>(h)->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd,
+                                                  mode, skip, scores, endQuery, endTarget, deviceMs);
+}
+
+void opalb200_db_last_stats(const OpalB200Db* h, int* kernelLaunches, int* rerun32, int* G, int* R, int* passes) {
+    const SearchStats& s = reinterpret_cast<const DeviceDb*>(h)->stats();
+    if (kernelLaunches) *kernelLaunches = s.kernelLaunches;
+    if (rerun32) *rerun32 = s.rerun32;
+    if (G) *G = s.G;
+    if (R) *R = s.R;
+    if (passes) *passes = s.passes;
+}
+
+double opalb200_measure_dpx_peak(int device, double* threadInstrPerSec, float* ms) {
+    return measure_dpx_peak(device, threadInstrPerSec, ms);
+}
+
+}  // extern "C"

@@ -1,0 +1,404 @@
+// engine.cu -- host-side engine: database packing, geometry choice, precision ladder, launches.
+//
+// Plays the role of the reference's escalation drivers searchDatabaseSW / searchDatabase<MODE>
+// (reference src/opal.cpp:496-535, 983-1021) and of lane refill (loadNextSequence, :472-490), but
+// scheduled for a GPU: the database is sorted by length once (longest first), adjacent targets
+// are paired into the two 16-bit lanes of a group, warps pull groups of similar length from a
+// global counter, and the 16 -> 32 bit escalation re-runs exactly the flagged targets.
+#include "engine.h"
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+
+#include "r_list.h"
+#include "search_kernel.cuh"
+
+namespace opalb200 {
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_lastError;
+void set_error(const std::string& msg) { g_lastError = msg; }
+const char* last_error() { return g_lastError.c_str(); }
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+            return false;                                                                    \
+        }                                                                                    \
+    } while (0)
+
+// ------------------------------------------------------------------ kernel registry
+#define OPAL_DECLARE_TABLE(R) const void* const* kernel_table_R##R();
+OPAL_R_LIST(OPAL_DECLARE_TABLE)
+#undef OPAL_DECLARE_TABLE
+
+const std::vector<KernelTable>& kernel_tables() {
+    static const std::vector<KernelTable> tables = {
+#define OPAL_TABLE_ENTRY(R) {R, kernel_table_R##R()},
+        OPAL_R_LIST(OPAL_TABLE_ENTRY)
+#undef OPAL_TABLE_ENTRY
+    };
+    return tables;
+}
+
+static int rpad_of(int R) { return ((R / 4) % 2 == 0) ? R + 4 : R; }  // thread stride: odd count of 16-byte units
+
+// Picks (G, R, passes) for a query of Q rows: minimise estimated issue slots per target column,
+// divided by how much of the GPU the resulting thread count can fill.
+static bool pick_geometry(int Q, int A, int lanes, long long numTargets, double avgLen, int smemLimit, int numSMs,
+                          int mode, Geometry* out) {
+    const double kCellCost = 7.5, kStepOverhead = 30.0;
+    const int planes = lanes == 2 ? 2 : 1;
+    const auto& tables = kernel_tables();
+    double bestCost = 1e300;
+    bool found = false;
+    const double groups = std::max(1.0, (double)numTargets / lanes);
+    for (size_t ti = 0; ti < tables.size(); ti++) {
+        const int R = tables[ti].R;
+        const int Rpad = rpad_of(R);
+        for (int G = 1; G <= 32; G *= 2) {
+            const int rowStride = (G * Rpad + 31) / 32 * 32;
+            const size_t smem = (size_t)planes * (A + 1) * rowStride * 4;
+            if (smem > (size_t)smemLimit) continue;
+            const int rows = G * R;
+            const int passes = (Q + rows - 1) / rows;
+            const double work = (double)passes * G * (R * kCellCost + kStepOverhead) * (avgLen + G - 1);
+            const double util = std::min(1.0, groups * G / ((double)numSMs * kBlockThreads));
+            const double cost = work / util;
+            if (cost < bestCost) {
+                bestCost = cost;
+                found = true;
+                out->G = G; out->R = R; out->tableIndex = (int)ti; out->passes = passes; out->Rpad = Rpad;
+                out->rowStride = rowStride; out->smemBytes = smem;
+                out->padTop = (mode == kModeNW) ? 0 : passes * rows - Q;
+            }
+        }
+    }
+    if (!found) set_error("alphabet too large for the shared-memory query profile");
+    return found;
+}
+
+// ------------------------------------------------------------------ DeviceDb
+DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        set_error("no usable CUDA device");
+        return nullptr;
+    }
+    DeviceDb* d = new DeviceDb();
+    d->device_ = device;
+    d->n_ = n;
+    auto fail = [&]() -> DeviceDb* { delete d; return nullptr; };
+    auto ok = [&]() -> bool {
+        CUDA_TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) { set_error("device is not sm_100 or newer"); return false; }
+        d->numSMs_ = prop.multiProcessorCount;
+        d->smemLimit_ = (int)prop.sharedMemPerBlockOptin;
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->stream_, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&d->evStart_));
+        CUDA_TRY(cudaEventCreate(&d->evStop_));
+
+        // ---- sort by length, longest first (counting sort; stable in caller order)
+        int maxLen = 0;
+        for (int i = 0; i < n; i++) {
+            if (lens[i] < 0) { set_error("negative sequence length"); return false; }
+            maxLen = std::max(maxLen, lens[i]);
+        }
+        d->order_.resize(n);
+        d->pos_.resize(n);
+        if (maxLen <= (1 << 22)) {
+            std::vector<int> start(maxLen + 2, 0);
+            for (int i = 0; i < n; i++) start[maxLen - lens[i] + 1]++;
+            for (int k = 1; k <= maxLen + 1; k++) start[k] += start[k - 1];
+            for (int i = 0; i < n; i++) d->order_[start[maxLen - lens[i]]++] = i;
+        } else {
+            for (int i = 0; i < n; i++) d->order_[i] = i;
+            std::stable_sort(d->order_.begin(), d->order_.end(), [&](int a, int b) { return lens[a] > lens[b]; });
+        }
+        d->sortedLen_.resize(n);
+        d->offsets_.resize((size_t)n + 1);
+        long long total = 0;
+        for (int p = 0; p < n; p++) {
+            const int i = d->order_[p];
+            d->pos_[i] = p;
+            d->sortedLen_[p] = lens[i];
+            d->offsets_[p] = total;
+            total += lens[i];
+        }
+        d->offsets_[n] = total;
+        d->totalResidues_ = total;
+
+        // ---- gather into pinned staging, in sorted order, on several host threads
+        const size_t bytes = (size_t)total + 64;
+        uint8_t* staging = nullptr;
+        CUDA_TRY(cudaMallocHost(&staging, bytes));
+        memset(staging + total, 0, 64);
+        int nThreads = (int)std::min<long long>(std::max(1u, std::thread::hardware_concurrency()), 1 + total / (1 << 20));
+        nThreads = std::max(1, std::min(nThreads, 32));
+        auto gather = [&](int lo, int hi) {
+            for (int p = lo; p < hi; p++)
+                if (d->sortedLen_[p] > 0) memcpy(staging + d->offsets_[p], db[d->order_[p]], (size_t)d->sortedLen_[p]);
+        };
+        if (nThreads == 1) gather(0, n);
+        else {
+            std::vector<std::thread> th;
+            int lo = 0;
+            for (int k = 0; k < nThreads; k++) {
+                const long long target = total * (k + 1) / nThreads;
+                int hi = (k == nThreads - 1) ? n : (int)(std::upper_bound(d->offsets_.begin(), d->offsets_.begin() + n, target) - d->offsets_.begin());
+                hi = std::max(hi, lo);
+                th.emplace_back(gather, lo, hi);
+                lo = hi;
+            }
+            for (auto& t : th) t.join();
+        }
+        CUDA_TRY(cudaMalloc(&d->dResidues_, bytes));
+        CUDA_TRY(cudaMemcpyAsync(d->dResidues_, staging, bytes, cudaMemcpyHostToDevice, d->stream_));
+        CUDA_TRY(cudaMalloc(&d->dOffsets_, sizeof(long long) * ((size_t)n + 1)));
+        CUDA_TRY(cudaMemcpyAsync(d->dOffsets_, d->offsets_.data(), sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, d->stream_));
+        const size_t nInts = sizeof(int) * (size_t)std::max(n, 1);
+        CUDA_TRY(cudaMalloc(&d->dLengths_, nInts));
+        CUDA_TRY(cudaMemcpyAsync(d->dLengths_, d->sortedLen_.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, d->stream_));
+        CUDA_TRY(cudaMalloc(&d->dScore_, nInts));
+        CUDA_TRY(cudaMalloc(&d->dEndQ_, nInts));
+        CUDA_TRY(cudaMalloc(&d->dEndT_, nInts));
+        CUDA_TRY(cudaMalloc(&d->dTaskList_, nInts));
+        CUDA_TRY(cudaMalloc(&d->dCounters_, sizeof(int) * 256));
+        CUDA_TRY(cudaMallocHost(&d->hScore_, nInts));
+        CUDA_TRY(cudaMallocHost(&d->hEndQ_, nInts));
+        CUDA_TRY(cudaMallocHost(&d->hEndT_, nInts));
+        CUDA_TRY(cudaStreamSynchronize(d->stream_));
+        CUDA_TRY(cudaFreeHost(staging));
+        return true;
+    }();
+    return ok ? d : fail();
+}
+
+DeviceDb::~DeviceDb() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    cudaFree(dResidues_); cudaFree(dOffsets_); cudaFree(dLengths_);
+    cudaFree(dScore_); cudaFree(dEndQ_); cudaFree(dEndT_); cudaFree(dTaskList_); cudaFree(dCounters_);
+    cudaFree(dBndH_); cudaFree(dBndF_);
+    cudaFreeHost(hScore_); cudaFreeHost(hEndQ_); cudaFreeHost(hEndT_);
+    if (evStart_) cudaEventDestroy(evStart_);
+    if (evStop_) cudaEventDestroy(evStop_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+bool DeviceDb::ensure_boundary() {
+    if (dBndH_) return true;
+    const size_t bytes = sizeof(uint32_t) * (size_t)(totalResidues_ + 64);
+    CUDA_TRY(cudaMalloc(&dBndH_, bytes));
+    CUDA_TRY(cudaMalloc(&dBndF_, bytes));
+    return true;
+}
+
+// Runs every pass of one precision class over `list` (sorted positions, longest first).
+int DeviceDb::run_class(int type, const std::vector<int>& list, const unsigned char* dQuery, const int* dMatrix, int Q,
+                        int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot) {
+    if (list.empty()) return 0;
+    const int lanes = type == 0 ? 2 : 1;
+    double avgLen = 0;
+    for (int p : list) avgLen += sortedLen_[p];
+    avgLen /= (double)list.size();
+    Geometry g;
+    if (!pick_geometry(Q, A, lanes, (long long)list.size(), avgLen, smemLimit_, numSMs_, mode, &g)) return OPAL_B200_ERR_CUDA;
+    if (g.passes > 1 && !ensure_boundary()) return OPAL_B200_ERR_CUDA;
+    if (*launchSlot + g.passes > 256) { set_error("too many passes"); return OPAL_B200_ERR_CUDA; }
+
+    const bool identity = (int)list.size() == n_;
+    auto okc = [&]() -> bool {
+        if (!identity)
+            CUDA_TRY(cudaMemcpyAsync(dTaskList_, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, stream_));
+        const int flavor = (mode == kModeSW) ? (wantEnd ? kFlavorSWEnd : kFlavorSWScore) : kFlavorGlobal;
+        const void* fn = kernel_tables()[g.tableIndex].fn[type * 3 + flavor];
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
+        for (int pass = 0; pass < g.passes; pass++) {
+            SearchParams p;
+            memset(&p, 0, sizeof(p));
+            p.query = dQuery; p.matrix = dMatrix; p.Q = Q; p.A = A; p.gapOpen = Go; p.gapExt = Ge; p.mode = mode;
+            p.wantEnd = wantEnd;
+            p.G = g.G; p.rowBase = pass * g.G * g.R; p.padTop = g.padTop; p.pass = pass; p.numPasses = g.passes;
+            p.rowStride = g.rowStride; p.Rpad = g.Rpad;
+            p.residues = dResidues_; p.offsets = dOffsets_; p.lengths = dLengths_;
+            p.taskList = identity ? nullptr : dTaskList_;
+            p.numTargets = (int)list.size();
+            p.counter = dCounters_ + (*launchSlot)++;
+            p.bndH = dBndH_; p.bndF = dBndF_;
+            p.outScore = dScore_; p.outEndQ = dEndQ_; p.outEndT = dEndT_;
+            p.overflowLimit = type == 0 ? 32767 - std::max(maxScore, 0) - 1 : (1 << 30);
+            p.padLetterScore = type == 0 ? -16384 : 0;
+            void* args[] = {&p};
+            const long long warpsNeeded = ((long long)list.size() / lanes * g.G + 31) / 32 + 1;
+            const int blocks = (int)std::max<long long>(1, std::min<long long>(numSMs_, (warpsNeeded + kBlockThreads / 32 - 1) / (kBlockThreads / 32)));
+            CUDA_TRY(cudaLaunchKernel(fn, dim3(blocks), dim3(kBlockThreads), args, g.smemBytes, stream_));
+            stats_.kernelLaunches++;
+        }
+        return true;
+    }();
+    if (!okc) return OPAL_B200_ERR_CUDA;
+    stats_.G = g.G; stats_.R = g.R; stats_.passes = g.passes;
+    return 0;
+}
+
+int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const int* matrix, int A, int wantEnd, int mode,
+                     const unsigned char* skip, int* scores, int* endQ, int* endT, float* deviceMs) {
+    stats_ = SearchStats();
+    if (deviceMs) *deviceMs = 0.f;
+    if (mode != kModeNW && mode != kModeHW && mode != kModeOV && mode != kModeSW) return OPAL_B200_ERR_MODE;
+    if (A <= 0 || A > 255) { set_error("alphabetLength must be in [1, 255]"); return OPAL_B200_ERR_CUDA; }
+    // Argument range of the widest pass (reference src/opal.cpp:183-198, 615-630).
+    if (Go <= INT_MIN / 2 || INT_MAX / 2 <= Go || Ge <= INT_MIN / 2 || INT_MAX / 2 <= Ge) return OPAL_B200_ERR_OVERFLOW;
+    int maxP = INT_MIN, minP = INT_MAX;
+    for (int i = 0; i < A * A; i++) {
+        if (matrix[i] <= INT_MIN / 2 || INT_MAX / 2 <= matrix[i]) return OPAL_B200_ERR_OVERFLOW;
+        maxP = std::max(maxP, matrix[i]);
+        minP = std::min(minP, matrix[i]);
+    }
+    const long long absP = std::max<long long>(std::llabs((long long)maxP), std::llabs((long long)minP));
+    const long long gapMax = std::max<long long>(std::llabs((long long)Go), std::llabs((long long)Ge));
+    if (Go < 0 || Ge < 0) { set_error("gap penalties must be non-negative"); return OPAL_B200_ERR_OVERFLOW; }
+    const bool args16 = absP <= 2048 && gapMax <= 2048;
+    const bool args32 = absP < (1 << 28) && gapMax < (1 << 28);
+    if (!args32) return OPAL_B200_ERR_OVERFLOW;  // beyond the widths this engine carries (documented deviation)
+
+    // ---- per-target routing
+    const bool isSW = mode == kModeSW;
+    // NW/HW/OV: every H, E, F of a (Q, T) problem lies in [-(3Go + (Q+T)Ge + |minP|), min(Q,T) maxP + Go].
+    auto fits = [&](int T, long long lim) -> bool {
+        const long long lo = 3LL * Go + ((long long)Q + T) * Ge + absP;
+        const long long hi = (maxP > 0 ? (long long)std::min(Q, T) * maxP : 0) + Go + absP;
+        return lo <= lim && hi <= lim;
+    };
+    std::vector<int> list16, list32;
+    bool touched = false;
+    for (int p = 0; p < n_; p++) {
+        const int i = order_[p];
+        if (skip && skip[i]) continue;
+        const int T = sortedLen_[p];
+        if (T == 0 || Q <= 0) {  // nothing to align: defined as in oracle/opal_oracle.c
+            int sc = 0, eq = Q - 1, et = T - 1;
+            if (Q > 0 && (mode == kModeNW || mode == kModeHW)) sc = -Go - (Q - 1) * Ge;
+            if (isSW) { eq = -1; et = -1; }
+            scores[i] = sc;
+            if (endQ) endQ[i] = wantEnd ? eq : -1;
+            if (endT) endT[i] = wantEnd ? et : -1;
+            continue;
+        }
+        touched = true;
+        if (isSW) {
+            if (args16) list16.push_back(p);
+            else if ((maxP > 0 ? (long long)std::min(Q, T) * maxP : 0) < (1LL << 30)) list32.push_back(p);
+            else return OPAL_B200_ERR_OVERFLOW;
+        } else {
+            if (args16 && fits(T, 28000)) list16.push_back(p);
+            else if (fits(T, 1LL << 30)) list32.push_back(p);
+            else return OPAL_B200_ERR_OVERFLOW;
+        }
+    }
+    if (!touched) return 0;
+
+    unsigned char* dQuery = nullptr;
+    int* dMatrix = nullptr;
+    int rc = 0;
+    auto body = [&]() -> bool {
+        CUDA_TRY(cudaSetDevice(device_));
+        CUDA_TRY(cudaMallocAsync(&dQuery, (size_t)Q + 16, stream_));
+        CUDA_TRY(cudaMallocAsync(&dMatrix, sizeof(int) * A * A, stream_));
+        CUDA_TRY(cudaMemcpyAsync(dQuery, query, (size_t)Q, cudaMemcpyHostToDevice, stream_));
+        CUDA_TRY(cudaMemcpyAsync(dMatrix, matrix, sizeof(int) * A * A, cudaMemcpyHostToDevice, stream_));
+        CUDA_TRY(cudaMemsetAsync(dCounters_, 0, sizeof(int) * 256, stream_));
+        int slot = 0;
+        CUDA_TRY(cudaEventRecord(evStart_, stream_));
+        auto fetch = [&]() -> bool {
+            const size_t nInts = sizeof(int) * (size_t)n_;
+            CUDA_TRY(cudaMemcpyAsync(hScore_, dScore_, nInts, cudaMemcpyDeviceToHost, stream_));
+            if (wantEnd) {
+                CUDA_TRY(cudaMemcpyAsync(hEndQ_, dEndQ_, nInts, cudaMemcpyDeviceToHost, stream_));
+                CUDA_TRY(cudaMemcpyAsync(hEndT_, dEndT_, nInts, cudaMemcpyDeviceToHost, stream_));
+            }
+            CUDA_TRY(cudaStreamSynchronize(stream_));
+            return true;
+        };
+        auto publish = [&](const std::vector<int>& list, std::vector<int>* overflowed) {
+            for (int p : list) {
+                const int i = order_[p];
+                const int sc = hScore_[p];
+                if (sc == kScoreOverflow || sc == kScoreNone) { if (overflowed) overflowed->push_back(p); else rc = OPAL_B200_ERR_OVERFLOW; continue; }
+                scores[i] = sc;
+                if (endQ) endQ[i] = (wantEnd && hEndQ_[p] != 0x7fffffff) ? hEndQ_[p] : -1;
+                if (endT) endT[i] = (wantEnd && hEndT_[p] != 0x7fffffff) ? hEndT_[p] : -1;
+            }
+        };
+        if (!list16.empty()) {
+            rc = run_class(0, list16, dQuery, dMatrix, Q, Go, Ge, A, wantEnd, mode, maxP, &slot);
+            if (rc) return rc != OPAL_B200_ERR_CUDA;
+            CUDA_TRY(cudaEventRecord(evStop_, stream_));
+            if (!fetch()) return false;
+            std::vector<int> again;
+            publish(list16, &again);
+            if (!again.empty()) {
+                stats_.rerun32 = (int)again.size();
+                std::vector<int> merged(list32.size() + again.size());
+                std::merge(list32.begin(), list32.end(), again.begin(), again.end(), merged.begin());
+                list32.swap(merged);
+            }
+        }
+        if (!list32.empty()) {
+            rc = run_class(1, list32, dQuery, dMatrix, Q, Go, Ge, A, wantEnd, mode, maxP, &slot);
+            if (rc) return rc != OPAL_B200_ERR_CUDA;
+            CUDA_TRY(cudaEventRecord(evStop_, stream_));
+            if (!fetch()) return false;
+            publish(list32, nullptr);
+        }
+        if (deviceMs) CUDA_TRY(cudaEventElapsedTime(deviceMs, evStart_, evStop_));
+        return true;
+    };
+    const bool okb = body();
+    if (dQuery) cudaFreeAsync(dQuery, stream_);
+    if (dMatrix) cudaFreeAsync(dMatrix, stream_);
+    if (!okb) return OPAL_B200_ERR_CUDA;
+    return rc;
+}
+
+// ------------------------------------------------------------------ DPX roofline probe
+double measure_dpx_peak(int device, double* threadInstrPerSec, float* msOut) {
+    constexpr int ILP = 8;
+    const int iters = 4096;
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return 0.0; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int blocks = prop.multiProcessorCount * 2;
+    uint32_t* out = nullptr;
+    if (cudaMalloc(&out, sizeof(uint32_t) * blocks * kBlockThreads) != cudaSuccess) { set_error("cudaMalloc failed"); return 0.0; }
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(a);
+        dpx_peak_kernel<ILP><<<blocks, kBlockThreads>>>(out, iters, 12345u + rep);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0) best = std::min(best, ms);
+    }
+    const cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return 0.0; }
+    const double instr = 6.0 * ILP * (double)iters * blocks * kBlockThreads;  // thread-level packed instructions
+    const double ips = instr / (best * 1e-3);
+    if (threadInstrPerSec) *threadInstrPerSec = ips;
+    if (msOut) *msOut = best;
+    return ips * 2.0 / 6.0 / 1e9;  // 2 cells per packed instruction, 6 instructions per SW cell pair
+}
+
+}  // namespace opalb200

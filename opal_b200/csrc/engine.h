@@ -1,0 +1,80 @@
+// engine.h -- host-side engine of opal-b200: resident database, geometry choice, pass scheduling.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace opalb200 {
+
+// Return codes shared with opal.h (OPAL_ERR_OVERFLOW / _NO_SIMD_SUPPORT / _INVALID_MODE).
+constexpr int OPAL_B200_ERR_OVERFLOW = 1, OPAL_B200_ERR_CUDA = 2, OPAL_B200_ERR_MODE = 3;
+
+// Kernel registry: one translation unit per strip height R (kernels_inst.cu compiled with
+// -DOPAL_R=<R>), each exporting a table indexed [type * 3 + flavor]; type 0 = Packed16, 1 = Scalar32.
+struct KernelTable {
+    int R;
+    const void* const* fn;
+};
+const std::vector<KernelTable>& kernel_tables();
+
+struct Geometry {
+    int G = 1, R = 0, tableIndex = 0, passes = 1, Rpad = 0, rowStride = 0, padTop = 0;
+    size_t smemBytes = 0;
+};
+
+struct SearchStats {
+    int kernelLaunches = 0, rerun32 = 0, G = 0, R = 0, passes = 0;
+};
+
+void set_error(const std::string& msg);
+const char* last_error();
+
+// A length-sorted (longest first) database resident in one device's HBM.
+class DeviceDb {
+public:
+    static DeviceDb* create(unsigned char* const* db, int n, const int* lens, int device);
+    ~DeviceDb();
+
+    // Score / score+end for every non-skipped target; outputs in caller order (-1 = unset).
+    int search(const unsigned char* query, int Q, int Go, int Ge, const int* matrix, int A, int wantEnd, int mode,
+               const unsigned char* skip, int* scores, int* endQ, int* endT, float* deviceMs);
+
+    int size() const { return n_; }
+    long long residues() const { return totalResidues_; }
+    const SearchStats& stats() const { return stats_; }
+    int device() const { return device_; }
+    cudaStream_t stream() const { return stream_; }
+    // sorted position -> caller index, and device-side views (used by the alignment stage)
+    const std::vector<int>& order() const { return order_; }
+    const std::vector<int>& sorted_position() const { return pos_; }
+    const uint8_t* d_residues() const { return dResidues_; }
+    const long long* d_offsets() const { return dOffsets_; }
+    const std::vector<long long>& offsets() const { return offsets_; }
+    const std::vector<int>& sorted_lengths() const { return sortedLen_; }
+
+private:
+    DeviceDb() {}
+    int run_class(int type, const std::vector<int>& list, const unsigned char* dQuery, const int* dMatrix, int Q, int Go,
+                  int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot);
+    bool ensure_boundary();
+
+    int device_ = 0, n_ = 0, numSMs_ = 0, smemLimit_ = 0;
+    long long totalResidues_ = 0;
+    std::vector<int> order_, pos_, sortedLen_;
+    std::vector<long long> offsets_;
+    uint8_t* dResidues_ = nullptr;
+    long long* dOffsets_ = nullptr;
+    int* dLengths_ = nullptr;
+    int *dScore_ = nullptr, *dEndQ_ = nullptr, *dEndT_ = nullptr, *dTaskList_ = nullptr, *dCounters_ = nullptr;
+    uint32_t *dBndH_ = nullptr, *dBndF_ = nullptr;
+    int *hScore_ = nullptr, *hEndQ_ = nullptr, *hEndT_ = nullptr;  // pinned
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t evStart_ = nullptr, evStop_ = nullptr;
+    SearchStats stats_;
+};
+
+double measure_dpx_peak(int device, double* threadInstrPerSec, float* ms);
+
+}  // namespace opalb200

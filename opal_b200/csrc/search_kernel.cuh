@@ -1,0 +1,424 @@
+// search_kernel.cuh -- the score / score+end kernel of opal-b200 (sm_100a).
+//
+// Replaces the reference's inter-sequence SIMD passes
+//   searchDatabaseSW_<SimdSW<T>>      (reference src/opal.cpp:164-470)
+//   searchDatabase_<Simd<T>, MODE>    (reference src/opal.cpp:594-977)
+// with one kernel template.  It is not a port of the lane-per-sequence column sweep: a GROUP of G
+// threads (G = 1..32, a power of two) owns one target pair and sweeps it as a systolic wavefront.
+//
+//   * thread t of the group holds R consecutive query rows in registers (H - gapOpen and E per
+//     row), so a group covers G*R query rows per pass; longer queries take several passes with
+//     the boundary row (H, F per target column) parked in HBM between passes;
+//   * at step s thread t computes target column s - t; the bottom (H, F) of its strip travels
+//     to thread t+1 with one __shfl_up_sync per value, so no DP state ever leaves registers
+//     within a pass;
+//   * the two 16-bit halves of every register hold two DIFFERENT targets (Rognes/Opal style), and
+//     the recurrence is issued as packed DPX instructions: VIADDMNMX.S16x2 (E, F, diagonal+max),
+//     VIMNMX.S16x2, VIADD.16x2;  the 32-bit re-run uses the s32 forms of the same instructions;
+//   * substitution scores come from a query profile in shared memory laid out thread-major
+//     (each thread's R rows contiguous, thread stride an odd number of 16-byte units) in two
+//     planes -- scores in the low half-word / in the high half-word -- so a packed score is
+//     LDS.128 + LDS.128 + one IMAD-pipe add per 4 rows, bank-conflict free for any residues.
+//
+// Arithmetic notes (all integer):
+//   HG = H - gapOpen is what is stored; the profile is pre-biased by +gapOpen, so
+//   diag + P == HG_diag + P'.  DPX adds wrap (they do not saturate), therefore 16-bit safety is
+//   established by bounds: SW flags a target whose best exceeds 32767 - maxScore - 1 (it is then
+//   re-run in 32 bits, mirroring the reference's char -> short -> int ladder, src/opal.cpp:512-530);
+//   NW/HW/OV targets are routed by an a-priori bound on the host (engine.cu).
+//
+// End-location key (reference src/opal.h:43-45 and SURVEY.md section 0 fact 3): maximal score, then
+// smallest target index, then smallest query index -- tracked per thread with strict improvements
+// in column-major order and merged across threads / passes with that key.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace opalb200 {
+
+constexpr int kBlockThreads = 512;
+constexpr int kModeNW = 0, kModeHW = 1, kModeOV = 2, kModeSW = 3;
+constexpr int kFlavorSWScore = 0, kFlavorSWEnd = 1, kFlavorGlobal = 2;
+constexpr int kScoreNone = INT32_MIN;          // "no candidate yet" in the running-result arrays
+constexpr int kScoreOverflow = INT32_MIN + 1;  // 16-bit pass: re-run this target in 32 bits
+
+struct SearchParams {
+    // query side
+    const uint8_t* query;  // Q alphabet indices
+    const int* matrix;     // A*A, row = query letter
+    int Q, A, gapOpen, gapExt, mode, wantEnd;
+    // geometry of this pass
+    int G, rowBase, padTop, pass, numPasses, rowStride, Rpad;
+    // database (length-sorted, concatenated, device resident)
+    const uint8_t* residues;
+    const long long* offsets;
+    const int* lengths;
+    // work: entries of taskList (or 0..numTargets-1 when null) are sorted-target indices
+    const int* taskList;
+    int numTargets;
+    int* counter;
+    // boundary row between passes, indexed by residue offset of the group's first target + column
+    void* bndH;
+    void* bndF;
+    // running results, indexed by sorted-target index
+    int* outScore;
+    int* outEndQ;
+    int* outEndT;
+    int overflowLimit;  // SW: largest best that is still provably exact at this width
+    int padLetterScore; // profile value of the pad letter (before the +gapOpen bias)
+};
+
+// Packed max with per-half "a is still the max" predicates (a >= b).
+// CUDA 12.9's __vibmax_s16x2 (crt/device_functions.hpp:964-983) declares its result "=r" without an
+// early clobber and re-reads operand a after writing it, so `x = __vibmax_s16x2(x, ...)` can be
+// assigned one register for both and then always reports "no improvement".  Same PTX, but the
+// result goes through a private temporary and the outputs are written last; ptxas still fuses it
+// into one VIMNMX.S16x2 with two predicate destinations.
+__device__ __forceinline__ uint32_t vibmax_s16x2(uint32_t a, uint32_t b, bool* pred_hi, bool* pred_lo) {
+    uint32_t val, ph, pl;
+    asm("{.reg .pred pu, pv;\n\t"
+        ".reg .s16 rs0, rs1, rs2, rs3;\n\t"
+        ".reg .b32 t;\n\t"
+        "max.s16x2 t, %3, %4;\n\t"
+        "mov.b32 {rs0, rs1}, t;\n\t"
+        "mov.b32 {rs2, rs3}, %3;\n\t"
+        "setp.eq.s16 pv, rs0, rs2;\n\t"
+        "setp.eq.s16 pu, rs1, rs3;\n\t"
+        "selp.b32 %1, 1, 0, pu;\n\t"
+        "selp.b32 %2, 1, 0, pv;\n\t"
+        "mov.b32 %0, t;}\n\t"
+        : "=&r"(val), "=&r"(ph), "=&r"(pl)
+        : "r"(a), "r"(b));
+    *pred_hi = (bool)ph;
+    *pred_lo = (bool)pl;
+    return val;
+}
+
+// ---------------------------------------------------------------- arithmetic traits
+struct Packed16 {
+    typedef uint32_t reg;
+    static constexpr int LANES = 2;
+    static constexpr int NEG = -30000;
+    static __device__ __forceinline__ reg splat(int v) { uint32_t u = (uint32_t)v & 0xffffu; return u | (u << 16); }
+    static __device__ __forceinline__ reg pack(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+    static __device__ __forceinline__ int lane(reg v, int l) { return l ? ((int)v >> 16) : (int)(short)(v & 0xffffu); }
+    static __device__ __forceinline__ reg addmax(reg a, reg b, reg c) { return __viaddmax_s16x2(a, b, c); }
+    static __device__ __forceinline__ reg addmax_relu(reg a, reg b, reg c) { return __viaddmax_s16x2_relu(a, b, c); }
+    static __device__ __forceinline__ reg vmax(reg a, reg b) { return __vmaxs2(a, b); }
+    static __device__ __forceinline__ reg vmax3(reg a, reg b, reg c) { return __vimax3_s16x2(a, b, c); }
+    static __device__ __forceinline__ reg add(reg a, reg b) { return __vadd2(a, b); }
+    static __device__ __forceinline__ reg bmax(reg a, reg b, bool* phi, bool* plo) { return vibmax_s16x2(a, b, phi, plo); }
+    static __device__ __forceinline__ reg combine(uint32_t lo, uint32_t hi) { return lo + hi; }
+};
+
+struct Scalar32 {
+    typedef int reg;
+    static constexpr int LANES = 1;
+    static constexpr int NEG = -1500000000;
+    static __device__ __forceinline__ reg splat(int v) { return v; }
+    static __device__ __forceinline__ reg pack(int lo, int) { return lo; }
+    static __device__ __forceinline__ int lane(reg v, int) { return v; }
+    static __device__ __forceinline__ reg addmax(reg a, reg b, reg c) { return __viaddmax_s32(a, b, c); }
+    static __device__ __forceinline__ reg addmax_relu(reg a, reg b, reg c) { return __viaddmax_s32_relu(a, b, c); }
+    static __device__ __forceinline__ reg vmax(reg a, reg b) { return max(a, b); }
+    static __device__ __forceinline__ reg vmax3(reg a, reg b, reg c) { return __vimax3_s32(a, b, c); }
+    static __device__ __forceinline__ reg add(reg a, reg b) { return a + b; }
+    static __device__ __forceinline__ reg bmax(reg a, reg b, bool* phi, bool* plo) { *phi = true; return __vibmax_s32(a, b, plo); }
+    static __device__ __forceinline__ reg combine(uint32_t lo, uint32_t) { return (int)lo; }
+};
+
+// Column -1 of the DP matrix (reference src/opal.cpp:247-249 for SW, :671-679 for the others);
+// rows above the query (padding, r < 0) and the corner behave as H = 0.
+__device__ __forceinline__ int border_h(int mode, int r, int Go, int Ge) {
+    if (mode == kModeSW || mode == kModeOV || r < 0) return 0;
+    return -Go - r * Ge;
+}
+
+// Lexicographic "is candidate (s, c, r) better than (S, C, R)" under the end-location key.
+__device__ __forceinline__ bool better(int s, int c, int r, int S, int C, int R) {
+    if (s != S) return s > S;
+    if (c != C) return c < C;
+    return r < R;
+}
+
+// ---------------------------------------------------------------- the kernel
+// Shared memory: plane LO = (A+1) rows x rowStride words, then plane HI likewise (Packed16 only).
+// Word (y, t*Rpad + j) of plane LO holds the biased score of padded query row rowBase + t*R + j
+// against target letter y in its low half-word (sign bits cleared); plane HI holds it shifted
+// left by 16.  Letter A is the "pad letter" used past the end of the shorter target of a pair.
+template <int R, int FLAVOR, class TR>
+__global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchParams p) {
+    typedef typename TR::reg reg;
+    constexpr int LANES = TR::LANES;
+    constexpr int NV = R / 4;  // 128-bit profile loads per plane per column
+    extern __shared__ __align__(16) uint32_t smem[];
+
+    const int G = p.G, Go = p.gapOpen, Ge = p.gapExt, A = p.A, mode = p.mode;
+    const int planeWords = (A + 1) * p.rowStride;
+
+    // ---- build the query profile for this pass
+    for (int idx = threadIdx.x; idx < planeWords; idx += blockDim.x) {
+        const int y = idx / p.rowStride, pos = idx - y * p.rowStride;
+        const int t = pos / p.Rpad, j = pos - t * p.Rpad;
+        int sc = Go;  // padding rows score 0 against everything (keeps H = 0 above the query)
+        if (t < G && j < R) {
+            const int r = p.rowBase + t * R + j - p.padTop;
+            if (r >= 0 && r < p.Q) sc = ((y < A) ? p.matrix[(int)p.query[r] * A + y] : p.padLetterScore) + Go;
+            else if (y == A) sc = p.padLetterScore + Go;
+        }
+        if (LANES == 2) {
+            smem[idx] = (uint32_t)sc & 0xffffu;
+            smem[planeWords + idx] = (uint32_t)sc << 16;
+        } else {
+            smem[idx] = (uint32_t)sc;
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int t = lane & (G - 1);
+    const int groupInWarp = lane / G;
+    const int groupsPerWarp = 32 / G;
+    const uint32_t* myLo = smem + t * p.Rpad;
+    const uint32_t* myHi = myLo + planeWords;
+    const reg negGe = TR::splat(-Ge), negGo = TR::splat(-Go);
+    const reg NEGV = TR::splat(TR::NEG);
+    const bool firstPass = p.pass == 0, lastPass = p.pass == p.numPasses - 1;
+    const int myRow0 = p.rowBase + t * R - p.padTop;  // query row of this thread's register 0
+    // NW keeps padding at the bottom, so its last query row sits at a run-time position.
+    const int lastRowPadded = p.Q - 1 + p.padTop;
+    const int tLast = (lastRowPadded - p.rowBase) / R, jLast = (lastRowPadded - p.rowBase) % R;
+
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(p.counter, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if ((long long)w * groupsPerWarp * LANES >= p.numTargets) break;
+
+        // ---- this group's targets
+        const int i0 = (w * groupsPerWarp + groupInWarp) * LANES;
+        int tgt[2] = {-1, -1}, T[2] = {0, 0};
+        const uint8_t* seq[2] = {p.residues, p.residues};
+        long long off0 = 0;
+#pragma unroll
+        for (int l = 0; l < LANES; l++) {
+            if (i0 + l < p.numTargets) {
+                tgt[l] = p.taskList ? p.taskList[i0 + l] : i0 + l;
+                T[l] = p.lengths[tgt[l]];
+                const long long o = p.offsets[tgt[l]];
+                seq[l] = p.residues + o;
+                if (l == 0) off0 = o;
+            }
+        }
+        const int Tmax = max(T[0], T[1]);
+        const int steps = __reduce_max_sync(0xffffffffu, Tmax > 0 ? Tmax + G - 1 : 0);
+
+        // ---- per-thread DP state: column -1
+        reg HG[R], E[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            HG[j] = TR::splat(border_h(mode, myRow0 + j, Go, Ge) - Go);
+            E[j] = NEGV;
+        }
+        reg diag = TR::splat(border_h(mode, myRow0 - 1, Go, Ge) - Go);
+        reg outH = NEGV, outF = NEGV;
+
+        // tracking state
+        reg best = TR::splat(FLAVOR == kFlavorGlobal ? TR::NEG : 0);  // SW: true H; global: HG of the last row
+        int rowLo = -1, rowHi = -1, colLo = -1, colHi = -1;          // SW end / HW-OV last-row column
+        int nwScore[2] = {kScoreNone, kScoreNone};                    // NW final cell
+        int lcScore[2] = {kScoreNone, kScoreNone}, lcRow[2] = {-1, -1};  // OV last column
+
+        // boundary prefetch for passes > 0 (thread 0 of the group only)
+        const reg* bH = reinterpret_cast<const reg*>(p.bndH) + off0;
+        const reg* bF = reinterpret_cast<const reg*>(p.bndF) + off0;
+        reg nextBH = NEGV, nextBF = NEGV;
+        if (!firstPass && t == 0 && Tmax > 0) { nextBH = bH[0]; nextBF = bF[0]; }
+        // residue prefetch
+        int c = -t;
+        int y0n = A, y1n = A;
+        if (c == 0) { if (T[0] > 0) y0n = seq[0][0]; if (LANES == 2 && T[1] > 0) y1n = seq[1][0]; }
+
+        for (int s = 0; s < steps; s++, c++) {
+            // ---- (H, F) of the row above, for column c
+            reg upH = __shfl_up_sync(0xffffffffu, outH, 1, G);
+            reg upF = __shfl_up_sync(0xffffffffu, outF, 1, G);
+            if (t == 0) {
+                if (firstPass) {
+                    upH = TR::splat((mode == kModeNW ? -Go - c * Ge : 0) - Go);  // row -1, reference :716-732
+                    upF = NEGV;
+                } else {
+                    upH = nextBH; upF = nextBF;
+                    if (c + 1 < Tmax) { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
+                }
+            }
+            const bool active = c >= 0 && c < Tmax;
+            const int y0 = y0n, y1 = y1n;
+            {   // prefetch the residues of the next column
+                const int cn = c + 1;
+                y0n = A; y1n = A;
+                if (cn >= 0) {
+                    if (cn < T[0]) y0n = seq[0][cn];
+                    if (LANES == 2 && cn < T[1]) y1n = seq[1][cn];
+                }
+            }
+            if (!active) continue;
+
+            const uint4* plo = reinterpret_cast<const uint4*>(myLo + y0 * p.rowStride);
+            const uint4* phi = reinterpret_cast<const uint4*>(myHi + y1 * p.rowStride);
+            reg d = diag, u = upH, f = upF;
+            diag = upH;
+            const reg bestBefore = best;
+            reg hprev = 0;
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                const uint4 a = plo[v];
+                uint4 b = a;
+                if (LANES == 2) b = phi[v];
+                const uint32_t al[4] = {a.x, a.y, a.z, a.w}, bl[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int j = v * 4 + k;
+                    const reg P = TR::combine(al[k], bl[k]);
+                    const reg hl = HG[j];
+                    const reg e = TR::addmax(E[j], negGe, hl);
+                    E[j] = e;
+                    f = TR::addmax(f, negGe, u);
+                    reg h;
+                    if (FLAVOR == kFlavorGlobal) h = TR::vmax(TR::addmax(d, P, e), f);
+                    else h = TR::vmax(TR::addmax_relu(d, P, e), f);
+                    if (FLAVOR == kFlavorSWScore) {
+                        if (j & 1) best = TR::vmax3(best, hprev, h); else hprev = h;
+                    } else if (FLAVOR == kFlavorSWEnd) {
+                        bool ph, pl;
+                        best = TR::bmax(best, h, &ph, &pl);
+                        if (!pl) rowLo = j;
+                        if (LANES == 2 && !ph) rowHi = j;
+                    }
+                    u = TR::add(h, negGo);
+                    d = hl;
+                    HG[j] = u;
+                }
+            }
+            if (FLAVOR == kFlavorSWScore && (R & 1)) best = TR::vmax(best, hprev);
+            outH = u; outF = f;
+
+            if (FLAVOR == kFlavorSWEnd) {
+                const reg ch = best ^ bestBefore;
+                if (LANES == 2) { if (ch & 0xffffu) colLo = c; if (ch >> 16) colHi = c; }
+                else if (ch) colLo = c;
+            }
+            if (FLAVOR == kFlavorGlobal) {
+                if (mode == kModeNW) {
+                    if (lastPass && t == tLast) {
+#pragma unroll
+                        for (int l = 0; l < LANES; l++)
+                            if (c == T[l] - 1) {
+                                reg v = HG[0];
+#pragma unroll
+                                for (int j = 1; j < R; j++) if (j == jLast) v = HG[j];
+                                nwScore[l] = TR::lane(v, l) + Go;
+                            }
+                    }
+                } else {
+                    // last query row (HW, OV): register R-1 of thread G-1 in the last pass
+                    if (lastPass && t == G - 1) {
+                        reg cand = u;
+                        if (LANES == 2) cand = TR::pack(c < T[0] ? TR::lane(u, 0) : TR::NEG, c < T[1] ? TR::lane(u, 1) : TR::NEG);
+                        bool ph, pl;
+                        best = TR::bmax(best, cand, &ph, &pl);
+                        if (!pl) colLo = c;
+                        if (LANES == 2 && !ph) colHi = c;
+                    }
+                    // last target column (OV): every real row of this thread
+                    if (mode == kModeOV) {
+#pragma unroll
+                        for (int l = 0; l < LANES; l++)
+                            if (c == T[l] - 1) {
+#pragma unroll
+                                for (int j = 0; j < R; j++) {
+                                    const int r = myRow0 + j;
+                                    const int v = TR::lane(HG[j], l) + Go;
+                                    if (r >= 0 && r < p.Q && v > lcScore[l]) { lcScore[l] = v; lcRow[l] = r; }
+                                }
+                            }
+                    }
+                }
+            }
+            if (!lastPass && t == G - 1) {
+                reinterpret_cast<reg*>(p.bndH)[off0 + c] = outH;
+                reinterpret_cast<reg*>(p.bndF)[off0 + c] = outF;
+            }
+        }
+
+        // ---- reduce the group's candidates and merge them into the running results
+#pragma unroll
+        for (int l = 0; l < LANES; l++) {
+            int sc = kScoreNone, cc = 0x7fffffff, rr = 0x7fffffff;  // this thread's candidate
+            if (FLAVOR != kFlavorGlobal) {
+                sc = TR::lane(best, l);
+                if (FLAVOR == kFlavorSWEnd && sc > 0) { cc = l ? colHi : colLo; rr = myRow0 + (l ? rowHi : rowLo); }
+            } else if (mode == kModeNW) {
+                sc = nwScore[l]; cc = T[l] - 1; rr = p.Q - 1;
+            } else {
+                if (lastPass && t == G - 1 && T[l] > 0) { sc = TR::lane(best, l) + Go; cc = l ? colHi : colLo; rr = p.Q - 1; }
+                if (mode == kModeOV && lcScore[l] != kScoreNone && better(lcScore[l], T[l] - 1, lcRow[l], sc, cc, rr)) {
+                    sc = lcScore[l]; cc = T[l] - 1; rr = lcRow[l];
+                }
+            }
+            for (int o = 1; o < G; o <<= 1) {
+                const int s2 = __shfl_xor_sync(0xffffffffu, sc, o);
+                const int c2 = __shfl_xor_sync(0xffffffffu, cc, o);
+                const int r2 = __shfl_xor_sync(0xffffffffu, rr, o);
+                if (better(s2, c2, r2, sc, cc, rr)) { sc = s2; cc = c2; rr = r2; }
+            }
+            if (t == 0 && tgt[l] >= 0) {
+                const int i = tgt[l];
+                const bool isSW = FLAVOR != kFlavorGlobal;
+                bool overflow = isSW && sc > p.overflowLimit;
+                if (!firstPass) {
+                    const int ps = p.outScore[i];
+                    if (ps == kScoreOverflow) overflow = true;
+                    else if (ps != kScoreNone && (sc == kScoreNone || better(ps, p.outEndT[i], p.outEndQ[i], sc, cc, rr))) {
+                        sc = ps; cc = p.outEndT[i]; rr = p.outEndQ[i];
+                    }
+                }
+                if (overflow) sc = kScoreOverflow;
+                if (sc != kScoreNone || firstPass) {
+                    p.outScore[i] = sc;
+                    const bool haveEnd = p.wantEnd && sc != kScoreOverflow && sc != kScoreNone && !(isSW && sc == 0);
+                    p.outEndT[i] = haveEnd ? cc : (isSW || sc == kScoreNone ? 0x7fffffff : cc);
+                    p.outEndQ[i] = haveEnd ? rr : (isSW || sc == kScoreNone ? 0x7fffffff : rr);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- DPX issue-rate probe
+// Register-only loop of the SW cell recurrence (6 packed instructions per 2 cells) used by
+// bench.py to measure the integer-pipe roofline on the device it runs on.
+template <int ILP>
+__global__ void __launch_bounds__(kBlockThreads, 1) dpx_peak_kernel(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t h[ILP], e[ILP], f[ILP], b[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; i++) { h[i] = seed + i * 0x00010001u + threadIdx.x; e[i] = h[i] ^ 0x00050003u; f[i] = e[i] + 0x00010002u; b[i] = 0; }
+    const uint32_t ng = 0xffffffffu, no = 0xfff5fff5u, pp = 0x00030002u;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < ILP; i++) {
+            e[i] = __viaddmax_s16x2(e[i], ng, h[i]);
+            f[i] = __viaddmax_s16x2(f[i], ng, h[i]);
+            uint32_t x = __viaddmax_s16x2_relu(h[i], pp, e[i]);
+            x = __vmaxs2(x, f[i]);
+            b[i] = __vmaxs2(b[i], x);
+            h[i] = __vadd2(x, no);
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; i++) acc ^= b[i] ^ h[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+}  // namespace opalb200

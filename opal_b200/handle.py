@@ -1,0 +1,101 @@
+"""Python mirror of include/opal_b200.h: the resident-database handle of libopal_b200.so.
+
+No CPU implementation exists: constructing :class:`OpalB200` raises if the CUDA library has not
+been built, and every search fails loudly (non-zero return code) when no sm_100 device is usable.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from .capi import MODES, OpalCLibrary, SequenceDB
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libopal_b200.so")
+
+
+class OpalB200(OpalCLibrary):
+    """libopal_b200.so: the opal.h entry points (inherited) plus the opal_b200.h extensions."""
+
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: build it with `make -C opal_b200/csrc` "
+                               "(or __graft_entry__.build()); opal-b200 has no CPU fallback")
+        super().__init__(path)
+        L, vp, ci = self.lib, ctypes.c_void_p, ctypes.c_int
+        L.opalb200_device_count.restype = ci
+        L.opalb200_last_error.restype = ctypes.c_char_p
+        L.opalb200_db_create.argtypes = [vp, ci, vp, ci]
+        L.opalb200_db_create.restype = vp
+        L.opalb200_db_destroy.argtypes = [vp]
+        L.opalb200_db_destroy.restype = None
+        L.opalb200_db_length.argtypes = [vp]
+        L.opalb200_db_length.restype = ci
+        L.opalb200_db_residues.argtypes = [vp]
+        L.opalb200_db_residues.restype = ctypes.c_longlong
+        L.opalb200_db_search.argtypes = [vp, vp, ci, ci, ci, vp, ci, ci, ci, vp, vp, vp, vp, vp]
+        L.opalb200_db_search.restype = ci
+        L.opalb200_db_last_stats.argtypes = [vp] + [ctypes.POINTER(ci)] * 5
+        L.opalb200_db_last_stats.restype = None
+        L.opalb200_measure_dpx_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]
+        L.opalb200_measure_dpx_peak.restype = ctypes.c_double
+
+    def device_count(self):
+        return int(self.lib.opalb200_device_count())
+
+    def last_error(self):
+        return self.lib.opalb200_last_error().decode()
+
+    def create_db(self, db: SequenceDB, device=0):
+        h = self.lib.opalb200_db_create(db.pointers.ctypes.data, len(db), db.lengths.ctypes.data, int(device))
+        if not h:
+            raise RuntimeError("opalb200_db_create failed: " + self.last_error())
+        return ResidentDb(self, h, len(db))
+
+    def measure_dpx_peak(self, device=0):
+        ips, ms = ctypes.c_double(0), ctypes.c_float(0)
+        g = self.lib.opalb200_measure_dpx_peak(int(device), ctypes.byref(ips), ctypes.byref(ms))
+        if g <= 0:
+            raise RuntimeError("DPX probe failed: " + self.last_error())
+        return float(g), float(ips.value), float(ms.value)
+
+
+class ResidentDb:
+    """A database packed once into one GPU's HBM (opalb200_db_create)."""
+
+    def __init__(self, eng: OpalB200, handle, n):
+        self.eng, self.handle, self.n = eng, handle, n
+
+    def search(self, query, gap_open, gap_ext, score_matrix, alphabet_length, search_type, mode, skip=None):
+        """Returns (rc, scores, endQuery, endTarget, device_ms); arrays are in caller order."""
+        query = np.ascontiguousarray(query, dtype=np.uint8)
+        sm = np.ascontiguousarray(score_matrix, dtype=np.int32).ravel()
+        sc = np.zeros(self.n, dtype=np.int32)
+        eq = np.full(self.n, -1, dtype=np.int32)
+        et = np.full(self.n, -1, dtype=np.int32)
+        ms = ctypes.c_float(0)
+        if isinstance(mode, str):
+            mode = MODES[mode]
+        skp = None if skip is None else np.ascontiguousarray(skip, dtype=np.uint8)
+        rc = self.eng.lib.opalb200_db_search(
+            self.handle, query.ctypes.data, int(query.size), int(gap_open), int(gap_ext), sm.ctypes.data,
+            int(alphabet_length), int(search_type), int(mode), None if skp is None else skp.ctypes.data,
+            sc.ctypes.data, eq.ctypes.data, et.ctypes.data, ctypes.byref(ms))
+        return rc, sc, eq, et, float(ms.value)
+
+    def last_stats(self):
+        v = [ctypes.c_int(0) for _ in range(5)]
+        self.eng.lib.opalb200_db_last_stats(self.handle, *[ctypes.byref(x) for x in v])
+        return dict(zip(("kernel_launches", "rerun32", "G", "R", "passes"), (x.value for x in v)))
+
+    def close(self):
+        if self.handle:
+            self.eng.lib.opalb200_db_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -34,5 +34,5 @@ def ref():
 @pytest.fixture(scope="session")
 def product():
     """The CUDA library through its C ABI. No fallback: a missing .so or device is a failure."""
-    from _util import PRODUCT_SO, OpalCLibrary
-    return OpalCLibrary(PRODUCT_SO)
+    from opal_b200.handle import OpalB200
+    return OpalB200()
