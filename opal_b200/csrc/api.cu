@@ -153,13 +153,15 @@ int opalb200_db_search(OpalB200Db* h, const unsigned char query[], int queryLeng
                                                   mode, skip, scores, endQuery, endTarget, deviceMs);
 }
 
-void opalb200_db_last_stats(const OpalB200Db* h, int* kernelLaunches, int* rerun32, int* G, int* R, int* passes) {
+void opalb200_db_last_stats(const OpalB200Db* h, int* kernelLaunches, int* rerun32, int* G, int* R, int* passes,
+                            int* warpsPerPartition) {
     const SearchStats& s = reinterpret_cast<const DeviceDb*>(h)->stats();
     if (kernelLaunches) *kernelLaunches = s.kernelLaunches;
     if (rerun32) *rerun32 = s.rerun32;
     if (G) *G = s.G;
     if (R) *R = s.R;
     if (passes) *passes = s.passes;
+    if (warpsPerPartition) *warpsPerPartition = s.warpsPerPartition;
 }
 
 double opalb200_measure_dpx_peak(int device, double* threadInstrPerSec, float* ms) {

@@ -46,18 +46,31 @@ const std::vector<KernelTable>& kernel_tables() {
     return tables;
 }
 
-static int rpad_of(int R) { return ((R / 4) % 2 == 0) ? R + 4 : R; }  // thread stride: odd count of 16-byte units
+// Thread stride in the profile: a multiple of 4 words (16-byte aligned LDS.128) with an odd number of
+// 16-byte units, so the 8 lanes of a quarter-warp hit 8 different bank groups whatever their residues are.
+static int rpad_of(int R) { const int r4 = (R + 3) / 4; return 4 * ((r4 % 2 == 0) ? r4 + 1 : r4); }
 
-// Picks (G, R, passes) for a query of Q rows: minimise estimated issue slots per target column,
-// divided by how much of the GPU the resulting thread count can fill.
-static bool pick_geometry(int Q, int A, int lanes, long long numTargets, double avgLen, int smemLimit, int numSMs,
-                          int mode, Geometry* out) {
-    const double kCellCost = 7.5, kStepOverhead = 30.0;
+// Picks (G, R, passes, warps per scheduler partition) for a query of Q rows.
+//
+// Timing model (cycles), calibrated against ncu runs (profiles/): the integer pipe retires one packed
+// DPX instruction per 2 cycles per partition, a cell pair costs ~5.5 of them, so a warp's step of R rows
+// takes about 11*R cycles of pipe time plus ~70 cycles of per-step overhead; k warps sharing a partition
+// interleave, so one step of one warp lasts max(k * 11 R, 11 R + 70).  Two bounds follow:
+//   throughput:  sum over warp-tasks of steps * stepTime / (partitions * k)
+//   tail:        the longest target's steps * stepTime  (it cannot be split across warps)
+// Small databases with a long tail (BASELINE configs[1]) are tail-bound and want G = 32 and k = 1;
+// large ones are throughput-bound and want few threads per target and k = 4.
+static bool pick_geometry(int Q, int A, int lanes, const std::vector<int>& lens, int smemLimit, int numSMs, int mode,
+                          Geometry* out) {
     const int planes = lanes == 2 ? 2 : 1;
     const auto& tables = kernel_tables();
     double bestCost = 1e300;
     bool found = false;
-    const double groups = std::max(1.0, (double)numTargets / lanes);
+    // sum of lengths and the longest length; lens is sorted longest first and tasks pair neighbours
+    double sumLen = 0;
+    for (size_t i = 0; i < lens.size(); i += lanes) sumLen += lens[i];
+    const double tasks = (double)((lens.size() + lanes - 1) / lanes);
+    const double maxLen = lens.empty() ? 0 : lens[0];
     for (size_t ti = 0; ti < tables.size(); ti++) {
         const int R = tables[ti].R;
         const int Rpad = rpad_of(R);
@@ -67,15 +80,41 @@ static bool pick_geometry(int Q, int A, int lanes, long long numTargets, double 
             if (smem > (size_t)smemLimit) continue;
             const int rows = G * R;
             const int passes = (Q + rows - 1) / rows;
-            const double work = (double)passes * G * (R * kCellCost + kStepOverhead) * (avgLen + G - 1);
-            const double util = std::min(1.0, groups * G / ((double)numSMs * kBlockThreads));
-            const double cost = work / util;
-            if (cost < bestCost) {
-                bestCost = cost;
-                found = true;
+            const double groupsPerWarp = 32.0 / G;
+            const double warpSteps = (sumLen + tasks * (G - 1)) / groupsPerWarp;  // per pass
+            const double warpTasks = std::max(1.0, tasks / groupsPerWarp);
+            for (int k = 1; k <= 4; k *= 2) {
+                // with fewer warp-tasks than resident warps the partitions are not shared k ways
+                const double kEff = std::max(1.0, std::min((double)k, std::ceil(warpTasks / (numSMs * 4.0))));
+                const double stepTime = std::max(kEff * 11.0 * R, 11.0 * R + 70.0);
+                const double warpsBusy = std::min((double)numSMs * 4 * k, warpTasks);
+                const double throughput = warpSteps * stepTime / warpsBusy;
+                const double tail = (maxLen + G - 1) * stepTime;
+                const double cost = passes * (std::max(throughput, tail) + 0.15 * std::min(throughput, tail) + 4000.0);
+                if (cost < bestCost) {
+                    bestCost = cost;
+                    found = true;
+                    out->G = G; out->R = R; out->tableIndex = (int)ti; out->passes = passes; out->Rpad = Rpad;
+                    out->rowStride = rowStride; out->smemBytes = smem; out->warpsPerPartition = k;
+                    out->padTop = (mode == kModeNW) ? 0 : passes * rows - Q;
+                }
+            }
+        }
+    }
+    // Development override: OPAL_B200_GEOMETRY="G,R,k" forces a geometry (ignored when it does not fit).
+    if (const char* env = getenv("OPAL_B200_GEOMETRY")) {
+        int G = 0, R = 0, k = 0;
+        if (sscanf(env, "%d,%d,%d", &G, &R, &k) == 3 && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && k >= 1 && k <= 4) {
+            for (size_t ti = 0; ti < tables.size(); ti++) {
+                if (tables[ti].R != R) continue;
+                const int Rpad = rpad_of(R), rowStride = (G * Rpad + 31) / 32 * 32;
+                const size_t smem = (size_t)planes * (A + 1) * rowStride * 4;
+                if (smem > (size_t)smemLimit) break;
+                const int rows = G * R, passes = (Q + rows - 1) / rows;
                 out->G = G; out->R = R; out->tableIndex = (int)ti; out->passes = passes; out->Rpad = Rpad;
-                out->rowStride = rowStride; out->smemBytes = smem;
+                out->rowStride = rowStride; out->smemBytes = smem; out->warpsPerPartition = k;
                 out->padTop = (mode == kModeNW) ? 0 : passes * rows - Q;
+                found = true;
             }
         }
     }
@@ -206,11 +245,10 @@ int DeviceDb::run_class(int type, const std::vector<int>& list, const unsigned c
                         int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot) {
     if (list.empty()) return 0;
     const int lanes = type == 0 ? 2 : 1;
-    double avgLen = 0;
-    for (int p : list) avgLen += sortedLen_[p];
-    avgLen /= (double)list.size();
+    std::vector<int> lens(list.size());
+    for (size_t k = 0; k < list.size(); k++) lens[k] = sortedLen_[list[k]];
     Geometry g;
-    if (!pick_geometry(Q, A, lanes, (long long)list.size(), avgLen, smemLimit_, numSMs_, mode, &g)) return OPAL_B200_ERR_CUDA;
+    if (!pick_geometry(Q, A, lanes, lens, smemLimit_, numSMs_, mode, &g)) return OPAL_B200_ERR_CUDA;
     if (g.passes > 1 && !ensure_boundary()) return OPAL_B200_ERR_CUDA;
     if (*launchSlot + g.passes > 256) { set_error("too many passes"); return OPAL_B200_ERR_CUDA; }
 
@@ -237,15 +275,16 @@ int DeviceDb::run_class(int type, const std::vector<int>& list, const unsigned c
             p.overflowLimit = type == 0 ? 32767 - std::max(maxScore, 0) - 1 : (1 << 30);
             p.padLetterScore = type == 0 ? -16384 : 0;
             void* args[] = {&p};
+            const int warpsPerBlock = 4 * g.warpsPerPartition;  // one block per SM, k warps per scheduler partition
             const long long warpsNeeded = ((long long)list.size() / lanes * g.G + 31) / 32 + 1;
-            const int blocks = (int)std::max<long long>(1, std::min<long long>(numSMs_, (warpsNeeded + kBlockThreads / 32 - 1) / (kBlockThreads / 32)));
-            CUDA_TRY(cudaLaunchKernel(fn, dim3(blocks), dim3(kBlockThreads), args, g.smemBytes, stream_));
+            const int blocks = (int)std::max<long long>(1, std::min<long long>(numSMs_, (warpsNeeded + warpsPerBlock - 1) / warpsPerBlock));
+            CUDA_TRY(cudaLaunchKernel(fn, dim3(blocks), dim3(32 * warpsPerBlock), args, g.smemBytes, stream_));
             stats_.kernelLaunches++;
         }
         return true;
     }();
     if (!okc) return OPAL_B200_ERR_CUDA;
-    stats_.G = g.G; stats_.R = g.R; stats_.passes = g.passes;
+    stats_.G = g.G; stats_.R = g.R; stats_.passes = g.passes; stats_.warpsPerPartition = g.warpsPerPartition;
     return 0;
 }
 

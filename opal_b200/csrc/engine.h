@@ -20,12 +20,12 @@ struct KernelTable {
 const std::vector<KernelTable>& kernel_tables();
 
 struct Geometry {
-    int G = 1, R = 0, tableIndex = 0, passes = 1, Rpad = 0, rowStride = 0, padTop = 0;
+    int G = 1, R = 0, tableIndex = 0, passes = 1, Rpad = 0, rowStride = 0, padTop = 0, warpsPerPartition = 4;
     size_t smemBytes = 0;
 };
 
 struct SearchStats {
-    int kernelLaunches = 0, rerun32 = 0, G = 0, R = 0, passes = 0;
+    int kernelLaunches = 0, rerun32 = 0, G = 0, R = 0, passes = 0, warpsPerPartition = 0;
 };
 
 void set_error(const std::string& msg);

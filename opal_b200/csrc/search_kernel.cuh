@@ -150,7 +150,6 @@ template <int R, int FLAVOR, class TR>
 __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchParams p) {
     typedef typename TR::reg reg;
     constexpr int LANES = TR::LANES;
-    constexpr int NV = R / 4;  // 128-bit profile loads per plane per column
     extern __shared__ __align__(16) uint32_t smem[];
 
     const int G = p.G, Go = p.gapOpen, Ge = p.gapExt, A = p.A, mode = p.mode;
@@ -181,7 +180,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
     const int groupsPerWarp = 32 / G;
     const uint32_t* myLo = smem + t * p.Rpad;
     const uint32_t* myHi = myLo + planeWords;
-    const reg negGe = TR::splat(-Ge), negGo = TR::splat(-Go);
+    const reg negGe = TR::splat(-Ge), negGo = TR::splat(-Go), negGmin = TR::splat(-min(Ge, Go));
     const reg NEGV = TR::splat(TR::NEG);
     const bool firstPass = p.pass == 0, lastPass = p.pass == p.numPasses - 1;
     const int myRow0 = p.rowBase + t * R - p.padTop;  // query row of this thread's register 0
@@ -189,10 +188,20 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
     const int lastRowPadded = p.Q - 1 + p.padTop;
     const int tLast = (lastRowPadded - p.rowBase) / R, jLast = (lastRowPadded - p.rowBase) % R;
 
+    // Work distribution: tasks are ordered longest first.  The first task of every warp is static and
+    // strided so that the longest targets land on different SMs / scheduler partitions (warp w of
+    // block b takes task w * gridDim.x + b); afterwards warps pull from a global counter (LPT order).
+    const int totalWarps = gridDim.x * (blockDim.x >> 5);
+    bool firstTask = true;
     for (;;) {
         int w = 0;
-        if (lane == 0) w = atomicAdd(p.counter, 1);
-        w = __shfl_sync(0xffffffffu, w, 0);
+        if (firstTask) {
+            w = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+            firstTask = false;
+        } else {
+            if (lane == 0) w = totalWarps + atomicAdd(p.counter, 1);
+            w = __shfl_sync(0xffffffffu, w, 0);
+        }
         if ((long long)w * groupsPerWarp * LANES >= p.numTargets) break;
 
         // ---- this group's targets
@@ -221,7 +230,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
             E[j] = NEGV;
         }
         reg diag = TR::splat(border_h(mode, myRow0 - 1, Go, Ge) - Go);
-        reg outH = NEGV, outF = NEGV;
+        reg outH = NEGV, outF = NEGV;  // bottom of this strip: (H - Go of its last row, F entering the row below)
 
         // tracking state
         reg best = TR::splat(FLAVOR == kFlavorGlobal ? TR::NEG : 0);  // SW: true H; global: HG of the last row
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
             if (t == 0) {
                 if (firstPass) {
                     upH = TR::splat((mode == kModeNW ? -Go - c * Ge : 0) - Go);  // row -1, reference :716-732
-                    upF = NEGV;
+                    upF = upH;  // F entering row 0 = max(-inf - Ge, H[-1][c] - Go)
                 } else {
                     upH = nextBH; upF = nextBF;
                     if (c + 1 < Tmax) { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
@@ -264,43 +273,68 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
             }
             if (!active) continue;
 
-            const uint4* plo = reinterpret_cast<const uint4*>(myLo + y0 * p.rowStride);
-            const uint4* phi = reinterpret_cast<const uint4*>(myHi + y1 * p.rowStride);
-            reg d = diag, u = upH, f = upF;
+            // ---- one target column for this thread's R query rows.
+            // Per cell (Gotoh, reference src/opal.cpp:280-328 / :748-772), with X = max(diag + P, E [, 0]):
+            //   H = max(X, F);  F' = max(F - Ge, H - Go) = max(F - min(Ge, Go), X - Go).
+            // So the only value carried from row to row is F (one VIADDMNMX per row on the critical
+            // path); E, X and X - Go of every row depend on the previous column only.  Row j+1's X is
+            // issued before row j's H is written back, which lets H - Go be updated in place.
+            const uint32_t* plo = myLo + y0 * p.rowStride;
+            const uint32_t* phi = myHi + y1 * p.rowStride;
+            reg P[R];
+            auto load_chunk = [&](int v) {  // rows 4v .. 4v+3 (fewer at the tail): LDS.128 / .64 / .32 per plane
+                const int j0 = v * 4;
+                if (j0 + 4 <= R) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(plo + j0);
+                    uint4 b = a;
+                    if (LANES == 2) b = *reinterpret_cast<const uint4*>(phi + j0);
+                    P[j0] = TR::combine(a.x, b.x); P[j0 + 1] = TR::combine(a.y, b.y);
+                    P[j0 + 2] = TR::combine(a.z, b.z); P[j0 + 3] = TR::combine(a.w, b.w);
+                } else {
+                    int j = j0;
+                    if (R - j >= 2) {
+                        const uint2 a = *reinterpret_cast<const uint2*>(plo + j);
+                        uint2 b = a;
+                        if (LANES == 2) b = *reinterpret_cast<const uint2*>(phi + j);
+                        P[j] = TR::combine(a.x, b.x); P[j + 1] = TR::combine(a.y, b.y);
+                        j += 2;
+                    }
+                    if (R - j >= 1) P[j] = TR::combine(plo[j], LANES == 2 ? phi[j] : 0u);
+                }
+            };
+            reg f = upF;
+            const reg dIn = diag;
             diag = upH;
             const reg bestBefore = best;
-            reg hprev = 0;
+            load_chunk(0);
+            reg e0 = TR::addmax(E[0], negGe, HG[0]);
+            E[0] = e0;
+            reg X = (FLAVOR == kFlavorGlobal) ? TR::addmax(dIn, P[0], e0) : TR::addmax_relu(dIn, P[0], e0);
+            reg Xprev = 0;
 #pragma unroll
-            for (int v = 0; v < NV; v++) {
-                const uint4 a = plo[v];
-                uint4 b = a;
-                if (LANES == 2) b = phi[v];
-                const uint32_t al[4] = {a.x, a.y, a.z, a.w}, bl[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int j = v * 4 + k;
-                    const reg P = TR::combine(al[k], bl[k]);
-                    const reg hl = HG[j];
-                    const reg e = TR::addmax(E[j], negGe, hl);
-                    E[j] = e;
-                    f = TR::addmax(f, negGe, u);
-                    reg h;
-                    if (FLAVOR == kFlavorGlobal) h = TR::vmax(TR::addmax(d, P, e), f);
-                    else h = TR::vmax(TR::addmax_relu(d, P, e), f);
-                    if (FLAVOR == kFlavorSWScore) {
-                        if (j & 1) best = TR::vmax3(best, hprev, h); else hprev = h;
-                    } else if (FLAVOR == kFlavorSWEnd) {
-                        bool ph, pl;
-                        best = TR::bmax(best, h, &ph, &pl);
-                        if (!pl) rowLo = j;
-                        if (LANES == 2 && !ph) rowHi = j;
-                    }
-                    u = TR::add(h, negGo);
-                    d = hl;
-                    HG[j] = u;
+            for (int j = 0; j < R; j++) {
+                reg Xn = 0;
+                if (j + 1 < R) {
+                    if ((j + 1) % 4 == 0) load_chunk((j + 1) / 4);
+                    const reg e1 = TR::addmax(E[j + 1], negGe, HG[j + 1]);
+                    E[j + 1] = e1;
+                    Xn = (FLAVOR == kFlavorGlobal) ? TR::addmax(HG[j], P[j + 1], e1) : TR::addmax_relu(HG[j], P[j + 1], e1);
                 }
+                if (FLAVOR == kFlavorSWScore) {
+                    if (j & 1) best = TR::vmax3(best, Xprev, X); else Xprev = X;
+                } else if (FLAVOR == kFlavorSWEnd) {
+                    bool ph, pl;
+                    best = TR::bmax(best, X, &ph, &pl);
+                    if (!pl) rowLo = j;
+                    if (LANES == 2 && !ph) rowHi = j;
+                }
+                const reg XG = TR::add(X, negGo);
+                HG[j] = TR::addmax(f, negGo, XG);   // H - Go = max(X, F) - Go
+                f = TR::addmax(f, negGmin, XG);     // F of the next row
+                X = Xn;
             }
-            if (FLAVOR == kFlavorSWScore && (R & 1)) best = TR::vmax(best, hprev);
+            if (FLAVOR == kFlavorSWScore && (R & 1)) best = TR::vmax(best, Xprev);
+            const reg u = HG[R - 1];
             outH = u; outF = f;
 
             if (FLAVOR == kFlavorSWEnd) {

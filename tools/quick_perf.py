@@ -27,7 +27,8 @@ def main():
     print(f"pack+upload {time.time()-t0:.3f}s")
     queries = [("P18080", q)]
     if which != "config2":
-        queries += [(f"Q{len(x)}", x) for x in datasets.config3_queries(sm)]
+        want = [int(x) for x in os.environ.get("QLENS", "144,375,1000,2005,5478").split(",")]
+        queries += [(f"Q{len(x)}", x) for x in datasets.config3_queries(sm) if len(x) in want]
     modes = ("SW", "NW", "HW", "OV") if which == "config2" else ("SW", "NW")
     for name, qq in queries:
         for mode in modes:
