@@ -11,7 +11,9 @@
 #include <climits>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 
 #include "r_list.h"
 #include "search_kernel.cuh"
@@ -44,6 +46,133 @@ const std::vector<KernelTable>& kernel_tables() {
 #undef OPAL_TABLE_ENTRY
     };
     return tables;
+}
+
+// ------------------------------------------------------------------ per-device resource cache
+// opalSearchDatabase packs and uploads its database on every call (the reference's signature takes
+// host pointers each time), so the CUDA allocations behind a call are recycled instead of being
+// returned to the driver: cudaMalloc / cudaMallocHost / stream and event creation cost far more
+// than the search itself on a 12k-sequence database.  Blocks are matched by size (first cached block
+// within 2x of the request); the cache is bounded and thread-safe.
+namespace {
+struct DeviceInfo { bool known = false; int numSMs = 0, smemLimit = 0, major = 0; };
+struct CachedBlock { void* p; size_t bytes; };
+struct ResourceCache {
+    std::mutex mu;
+    std::vector<CachedBlock> freeDevice[16], freePinned;
+    std::unordered_map<void*, size_t> liveBytes;
+    std::vector<cudaStream_t> streams[16];
+    std::vector<cudaEvent_t> events[16];
+    DeviceInfo info[16];
+    size_t cachedDevice[16] = {0}, cachedPinned = 0;
+};
+ResourceCache& cache() { static ResourceCache* c = new ResourceCache(); return *c; }  // leaked on purpose: no teardown order issues
+constexpr size_t kMaxCachedDevice = 8ull << 30, kMaxCachedPinned = 2ull << 30;
+
+bool take_block(std::vector<CachedBlock>& list, size_t bytes, void** out, size_t* got) {
+    size_t best = list.size();
+    for (size_t i = 0; i < list.size(); i++)
+        if (list[i].bytes >= bytes && list[i].bytes <= 2 * bytes + (1 << 16) && (best == list.size() || list[i].bytes < list[best].bytes)) best = i;
+    if (best == list.size()) return false;
+    *out = list[best].p; *got = list[best].bytes;
+    list[best] = list.back(); list.pop_back();
+    return true;
+}
+}  // namespace
+
+static bool device_alloc(int device, void** p, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 256);
+    ResourceCache& c = cache();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        size_t got = 0;
+        if (take_block(c.freeDevice[device & 15], bytes, p, &got)) { c.cachedDevice[device & 15] -= got; c.liveBytes[*p] = got; return true; }
+    }
+    CUDA_TRY(cudaMalloc(p, bytes));
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.liveBytes[*p] = bytes;
+    return true;
+}
+static void device_release(int device, void* p) {
+    if (!p) return;
+    ResourceCache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    const size_t bytes = c.liveBytes[p];
+    c.liveBytes.erase(p);
+    if (c.cachedDevice[device & 15] + bytes > kMaxCachedDevice) { cudaFree(p); return; }
+    c.freeDevice[device & 15].push_back({p, bytes});
+    c.cachedDevice[device & 15] += bytes;
+}
+static bool pinned_alloc(void** p, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 256);
+    ResourceCache& c = cache();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        size_t got = 0;
+        if (take_block(c.freePinned, bytes, p, &got)) { c.cachedPinned -= got; c.liveBytes[*p] = got; return true; }
+    }
+    CUDA_TRY(cudaMallocHost(p, bytes));
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.liveBytes[*p] = bytes;
+    return true;
+}
+static void pinned_release(void* p) {
+    if (!p) return;
+    ResourceCache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    const size_t bytes = c.liveBytes[p];
+    c.liveBytes.erase(p);
+    if (c.cachedPinned + bytes > kMaxCachedPinned) { cudaFreeHost(p); return; }
+    c.freePinned.push_back({p, bytes});
+    c.cachedPinned += bytes;
+}
+static bool stream_acquire(int device, cudaStream_t* s) {
+    ResourceCache& c = cache();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto& v = c.streams[device & 15];
+        if (!v.empty()) { *s = v.back(); v.pop_back(); return true; }
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
+    return true;
+}
+static void stream_release(int device, cudaStream_t s) {
+    if (!s) return;
+    ResourceCache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.streams[device & 15].push_back(s);
+}
+static bool event_acquire(int device, cudaEvent_t* e) {
+    ResourceCache& c = cache();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto& v = c.events[device & 15];
+        if (!v.empty()) { *e = v.back(); v.pop_back(); return true; }
+    }
+    CUDA_TRY(cudaEventCreate(e));
+    return true;
+}
+static void event_release(int device, cudaEvent_t e) {
+    if (!e) return;
+    ResourceCache& c = cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.events[device & 15].push_back(e);
+}
+static bool device_info(int device, DeviceInfo* out) {
+    ResourceCache& c = cache();
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (c.info[device & 15].known) { *out = c.info[device & 15]; return true; }
+    }
+    DeviceInfo di;
+    CUDA_TRY(cudaDeviceGetAttribute(&di.numSMs, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&di.smemLimit, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&di.major, cudaDevAttrComputeCapabilityMajor, device));
+    di.known = true;
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.info[device & 15] = di;
+    *out = di;
+    return true;
 }
 
 // Thread stride in the profile: a multiple of 4 words (16-byte aligned LDS.128) with an odd number of
@@ -135,14 +264,12 @@ DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int
     auto fail = [&]() -> DeviceDb* { delete d; return nullptr; };
     auto ok = [&]() -> bool {
         CUDA_TRY(cudaSetDevice(device));
-        cudaDeviceProp prop;
-        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-        if (prop.major < 10) { set_error("device is not sm_100 or newer"); return false; }
-        d->numSMs_ = prop.multiProcessorCount;
-        d->smemLimit_ = (int)prop.sharedMemPerBlockOptin;
-        CUDA_TRY(cudaStreamCreateWithFlags(&d->stream_, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreate(&d->evStart_));
-        CUDA_TRY(cudaEventCreate(&d->evStop_));
+        DeviceInfo di;
+        if (!device_info(device, &di)) return false;
+        if (di.major < 10) { set_error("device is not sm_100 or newer"); return false; }
+        d->numSMs_ = di.numSMs;
+        d->smemLimit_ = di.smemLimit;
+        if (!stream_acquire(device, &d->stream_) || !event_acquire(device, &d->evStart_) || !event_acquire(device, &d->evStop_)) return false;
 
         // ---- sort by length, longest first (counting sort; stable in caller order)
         int maxLen = 0;
@@ -177,7 +304,7 @@ DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int
         // ---- gather into pinned staging, in sorted order, on several host threads
         const size_t bytes = (size_t)total + 64;
         uint8_t* staging = nullptr;
-        CUDA_TRY(cudaMallocHost(&staging, bytes));
+        if (!pinned_alloc((void**)&staging, bytes)) return false;
         memset(staging + total, 0, 64);
         int nThreads = (int)std::min<long long>(std::max(1u, std::thread::hardware_concurrency()), 1 + total / (1 << 20));
         nThreads = std::max(1, std::min(nThreads, 32));
@@ -198,23 +325,23 @@ DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int
             }
             for (auto& t : th) t.join();
         }
-        CUDA_TRY(cudaMalloc(&d->dResidues_, bytes));
+        if (!device_alloc(device, (void**)&d->dResidues_, bytes)) return false;
         CUDA_TRY(cudaMemcpyAsync(d->dResidues_, staging, bytes, cudaMemcpyHostToDevice, d->stream_));
-        CUDA_TRY(cudaMalloc(&d->dOffsets_, sizeof(long long) * ((size_t)n + 1)));
+        if (!device_alloc(device, (void**)&d->dOffsets_, sizeof(long long) * ((size_t)n + 1))) return false;
         CUDA_TRY(cudaMemcpyAsync(d->dOffsets_, d->offsets_.data(), sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, d->stream_));
         const size_t nInts = sizeof(int) * (size_t)std::max(n, 1);
-        CUDA_TRY(cudaMalloc(&d->dLengths_, nInts));
+        if (!device_alloc(device, (void**)&d->dLengths_, nInts)) return false;
         CUDA_TRY(cudaMemcpyAsync(d->dLengths_, d->sortedLen_.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, d->stream_));
-        CUDA_TRY(cudaMalloc(&d->dScore_, nInts));
-        CUDA_TRY(cudaMalloc(&d->dEndQ_, nInts));
-        CUDA_TRY(cudaMalloc(&d->dEndT_, nInts));
-        CUDA_TRY(cudaMalloc(&d->dTaskList_, nInts));
-        CUDA_TRY(cudaMalloc(&d->dCounters_, sizeof(int) * 256));
-        CUDA_TRY(cudaMallocHost(&d->hScore_, nInts));
-        CUDA_TRY(cudaMallocHost(&d->hEndQ_, nInts));
-        CUDA_TRY(cudaMallocHost(&d->hEndT_, nInts));
+        if (!device_alloc(device, (void**)&d->dScore_, nInts)) return false;
+        if (!device_alloc(device, (void**)&d->dEndQ_, nInts)) return false;
+        if (!device_alloc(device, (void**)&d->dEndT_, nInts)) return false;
+        if (!device_alloc(device, (void**)&d->dTaskList_, nInts)) return false;
+        if (!device_alloc(device, (void**)&d->dCounters_, sizeof(int) * 256)) return false;
+        if (!pinned_alloc((void**)&d->hScore_, nInts)) return false;
+        if (!pinned_alloc((void**)&d->hEndQ_, nInts)) return false;
+        if (!pinned_alloc((void**)&d->hEndT_, nInts)) return false;
         CUDA_TRY(cudaStreamSynchronize(d->stream_));
-        CUDA_TRY(cudaFreeHost(staging));
+        pinned_release(staging);
         return true;
     }();
     return ok ? d : fail();
@@ -223,20 +350,17 @@ DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int
 DeviceDb::~DeviceDb() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
-    cudaFree(dResidues_); cudaFree(dOffsets_); cudaFree(dLengths_);
-    cudaFree(dScore_); cudaFree(dEndQ_); cudaFree(dEndT_); cudaFree(dTaskList_); cudaFree(dCounters_);
-    cudaFree(dBndH_); cudaFree(dBndF_);
-    cudaFreeHost(hScore_); cudaFreeHost(hEndQ_); cudaFreeHost(hEndT_);
-    if (evStart_) cudaEventDestroy(evStart_);
-    if (evStop_) cudaEventDestroy(evStop_);
-    if (stream_) cudaStreamDestroy(stream_);
+    void* dev[] = {dResidues_, dOffsets_, dLengths_, dScore_, dEndQ_, dEndT_, dTaskList_, dCounters_, dBndH_, dBndF_, dQuery_, dMatrix_};
+    for (void* p : dev) device_release(device_, p);
+    pinned_release(hScore_); pinned_release(hEndQ_); pinned_release(hEndT_);
+    event_release(device_, evStart_); event_release(device_, evStop_);
+    stream_release(device_, stream_);
 }
 
 bool DeviceDb::ensure_boundary() {
     if (dBndH_) return true;
     const size_t bytes = sizeof(uint32_t) * (size_t)(totalResidues_ + 64);
-    CUDA_TRY(cudaMalloc(&dBndH_, bytes));
-    CUDA_TRY(cudaMalloc(&dBndF_, bytes));
+    if (!device_alloc(device_, (void**)&dBndH_, bytes) || !device_alloc(device_, (void**)&dBndF_, bytes)) return false;
     return true;
 }
 
@@ -350,8 +474,13 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
     int rc = 0;
     auto body = [&]() -> bool {
         CUDA_TRY(cudaSetDevice(device_));
-        CUDA_TRY(cudaMallocAsync(&dQuery, (size_t)Q + 16, stream_));
-        CUDA_TRY(cudaMallocAsync(&dMatrix, sizeof(int) * A * A, stream_));
+        if ((size_t)Q + 16 > queryCapacity_) {
+            device_release(device_, dQuery_); dQuery_ = nullptr;
+            queryCapacity_ = std::max<size_t>(4096, 2 * ((size_t)Q + 16));
+            if (!device_alloc(device_, (void**)&dQuery_, queryCapacity_)) return false;
+        }
+        if (!dMatrix_ && !device_alloc(device_, (void**)&dMatrix_, sizeof(int) * 256 * 256)) return false;
+        dQuery = dQuery_; dMatrix = dMatrix_;
         CUDA_TRY(cudaMemcpyAsync(dQuery, query, (size_t)Q, cudaMemcpyHostToDevice, stream_));
         CUDA_TRY(cudaMemcpyAsync(dMatrix, matrix, sizeof(int) * A * A, cudaMemcpyHostToDevice, stream_));
         CUDA_TRY(cudaMemsetAsync(dCounters_, 0, sizeof(int) * 256, stream_));
@@ -402,8 +531,6 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
         return true;
     };
     const bool okb = body();
-    if (dQuery) cudaFreeAsync(dQuery, stream_);
-    if (dMatrix) cudaFreeAsync(dMatrix, stream_);
     if (!okb) return OPAL_B200_ERR_CUDA;
     return rc;
 }

@@ -69,6 +69,9 @@ private:
     int* dLengths_ = nullptr;
     int *dScore_ = nullptr, *dEndQ_ = nullptr, *dEndT_ = nullptr, *dTaskList_ = nullptr, *dCounters_ = nullptr;
     uint32_t *dBndH_ = nullptr, *dBndF_ = nullptr;
+    unsigned char* dQuery_ = nullptr;
+    int* dMatrix_ = nullptr;
+    size_t queryCapacity_ = 0;
     int *hScore_ = nullptr, *hEndQ_ = nullptr, *hEndT_ = nullptr;  // pinned
     cudaStream_t stream_ = nullptr;
     cudaEvent_t evStart_ = nullptr, evStop_ = nullptr;

@@ -1,0 +1,154 @@
+"""GPU parity for OPAL_SEARCH_ALIGNMENT: start location and operation string.
+
+SW is compared bit for bit with the golden vectors of the unmodified reference and with the oracle
+(the reference is trustworthy there).  NW/HW/OV are compared bit for bit
+with the oracle's literal restatement of findAlignment wherever that restatement yields a consistent
+alignment, and are validated semantically (replay, reference src/test.cpp:348-422) everywhere.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from _util import (MODES, OPAL_OVERFLOW_BUCKETS, OPAL_OVERFLOW_SIMPLE, ORACLE_SO, README_DB, README_MATRIX,
+                   README_QUERY, SequenceDB, dump_results, free_alignments, get_alignment, glibc_testcpp_data,
+                   new_results, search_dump)
+from opal_b200 import datasets, matrices
+from opal_b200.capi import OpalSearchResultStruct
+from test_oracle_golden import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def replay_code(oracle, q, t, res, i, go, ge, m, a):
+    """oracle_check_alignment on record i (0 = valid)."""
+    fn = oracle.lib.oracle_check_alignment
+    fn.restype = ctypes.c_int
+    rec = OpalSearchResultStruct.from_buffer_copy(res[i:i + 1].tobytes())
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    t = np.ascontiguousarray(t, dtype=np.uint8)
+    m = np.ascontiguousarray(m, dtype=np.int32)
+    return fn(ctypes.c_void_p(q.ctypes.data), len(q), ctypes.c_void_p(t.ctypes.data), len(t), ctypes.byref(rec),
+              go, ge, ctypes.c_void_p(m.ctypes.data), a)
+
+
+@pytest.mark.parametrize("mode", ["NW", "HW", "OV", "SW"])
+def test_readme_alignments(product, mode):
+    g = golden("readme.json")
+    db = SequenceDB.from_sequences(README_DB)
+    for ovf in (OPAL_OVERFLOW_SIMPLE, OPAL_OVERFLOW_BUCKETS):
+        rc, d = search_dump(product, README_QUERY, db, 3, 1, README_MATRIX, 4, 2, MODES[mode], ovf)
+        assert rc == 0
+        assert d == g[f"{mode}/2/{ovf}"]["results"]
+
+
+def test_config1_sw_alignments(product):
+    g = golden("config1.json")
+    b50 = matrices.blosum50()
+    rc, d = search_dump(product, np.array(g["query"], dtype=np.uint8), SequenceDB.from_sequences(g["db"]),
+                        3, 1, b50.flat(), 24, 2, MODES["SW"], OPAL_OVERFLOW_BUCKETS)
+    assert rc == 0
+    assert d == g["SW/2"]["results"]
+
+
+def test_protein_sw_alignments(product):
+    g = golden("protein.json")
+    b62 = matrices.blosum62()
+    rc, d = search_dump(product, np.array(g["query"], dtype=np.uint8), SequenceDB.from_sequences(g["db"]),
+                        11, 1, b62.flat(), 23, 2, MODES["SW"], OPAL_OVERFLOW_BUCKETS)
+    assert rc == 0
+    assert d == g["SW/2"]["results"]
+
+
+def test_reference_selftest_sw_alignments(product):
+    """./test SW of the reference (src/test.cpp): all 200 alignments, compared by digest."""
+    g = golden("testcpp.json")["SW"]
+    q, db = glibc_testcpp_data()
+    m = matrices.simple(4, 3, -1).flat()
+    rc, d = search_dump(product, q, db, 11, 1, m, 4, 2, MODES["SW"], OPAL_OVERFLOW_SIMPLE, digest=True)
+    assert rc == 0
+    assert d == g["results"]
+
+
+@pytest.mark.parametrize("mode", ["NW", "HW", "OV"])
+def test_reference_selftest_global_alignments(product, oracle, mode):
+    """./test NW|HW|OV: score/end/start must equal the reference's; the operations must replay to the score
+    (the reference's own acceptance test, src/test.cpp:166-167)."""
+    g = golden("testcpp.json")[mode]
+    q, db = glibc_testcpp_data()
+    m = matrices.simple(4, 3, -1).flat()
+    rc, res = product.search_database(q, db, 11, 1, m, 4, None, 2, MODES[mode], OPAL_OVERFLOW_SIMPLE)
+    assert rc == 0
+    d = dump_results(res, digest=True)
+    for i in range(len(db)):
+        assert replay_code(oracle, q, db.sequence(i), res, i, 11, 1, m, 4) == 0, (mode, i)
+    free_alignments(res)
+    assert [r[:6] for r in d] == [r[:6] for r in g["results"]]
+    assert d == g["results"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("mode", ["NW", "HW", "OV", "SW"])
+def test_random_alignments_vs_oracle(product, oracle, mode, seed):
+    """Random short / skewed pairs (where the reference itself crashes on a few per cent, SURVEY.md 8c
+    Q9-Q10): every alignment must replay; it must equal the oracle's whenever the oracle's replays."""
+    rng = np.random.default_rng(4000 + seed)
+    protein = seed % 2 == 0
+    if protein:
+        sm = matrices.blosum62()
+        go, ge, m, a = 11, 1, sm.flat(), 23
+        q = datasets.random_residues(int(rng.integers(1, 150)), rng, sm)
+        seqs = [datasets.random_residues(int(rng.integers(1, 200)), rng, sm) for _ in range(60)]
+        for i in range(0, 60, 6):
+            seqs[i] = datasets.mutate(q, 0.7, rng, sm)
+    else:
+        a = int(rng.integers(2, 5))
+        ge = int(rng.integers(1, 3))
+        go = int(rng.integers(2 * ge, 2 * ge + 6))
+        m = matrices.simple(a, int(rng.integers(1, 5)), -int(rng.integers(0, 4))).flat()
+        q = rng.integers(0, a, int(rng.integers(1, 60))).astype(np.uint8)
+        seqs = [rng.integers(0, a, int(rng.integers(1, 80))).astype(np.uint8) for _ in range(60)]
+    db = SequenceDB.from_sequences(seqs)
+    rc, got = product.search_database(q, db, go, ge, m, a, None, 2, MODES[mode], OPAL_OVERFLOW_SIMPLE)
+    rc2, want = oracle.search_database(q, db, go, ge, m, a, None, 2, MODES[mode], OPAL_OVERFLOW_SIMPLE)
+    assert rc == 0 and rc2 == 0
+    dg, dw = dump_results(got), dump_results(want)
+    same = 0
+    for i in range(len(db)):
+        has_alignment = not (mode == "SW" and got["score"][i] == 0)
+        if has_alignment:
+            assert replay_code(oracle, q, db.sequence(i), got, i, go, ge, m, a) == 0, (mode, i, dg[i])
+        assert dg[i][:4] == dw[i][:4], (mode, i)
+        oracle_valid = (not has_alignment) or replay_code(oracle, q, db.sequence(i), want, i, go, ge, m, a) == 0
+        if oracle_valid:
+            assert dg[i] == dw[i], (mode, i, dg[i], dw[i])
+            same += 1
+    assert same >= len(db) * (0.95 if mode == "SW" else 0.5)
+    free_alignments(got)
+    free_alignments(want)
+
+
+def test_alignment_from_prefilled_results(product):
+    """The reuse / "rescore" path (src/opal.cpp:1446-1451): score+end first, alignment added later."""
+    g = golden("api.json")
+    db = SequenceDB.from_sequences(README_DB)
+    res = new_results(4)
+    args = (README_QUERY, db, 3, 1, README_MATRIX, 4, res)
+    product.search_database(*args, 1, MODES["SW"], OPAL_OVERFLOW_SIMPLE)
+    product.search_database(*args, 2, MODES["SW"], OPAL_OVERFLOW_SIMPLE, entry="opalSearchDatabaseRescore")
+    assert dump_results(res) == g["reuse_then_alignment"]
+    free_alignments(res)
+
+
+def test_long_query_alignment_multi_pass(product, oracle):
+    """Alignment rectangles taller than one 256-row pass of the alignment kernel."""
+    rng = np.random.default_rng(77)
+    sm = matrices.blosum62()
+    q = datasets.random_residues(700, rng, sm)
+    seqs = [datasets.mutate(q, 0.85, rng, sm), datasets.mutate(q[100:650], 0.9, rng, sm), datasets.random_residues(300, rng, sm)]
+    db = SequenceDB.from_sequences(seqs)
+    for mode in ("SW", "NW"):
+        rc, got = search_dump(product, q, db, 11, 1, sm.flat(), 23, 2, MODES[mode])
+        rc2, want = search_dump(oracle, q, db, 11, 1, sm.flat(), 23, 2, MODES[mode])
+        assert rc == rc2 == 0
+        assert got == want, mode
