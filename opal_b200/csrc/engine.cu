@@ -251,6 +251,30 @@ static bool pick_geometry(int Q, int A, int lanes, const std::vector<int>& lens,
     return found;
 }
 
+// ---------------------------------------------------------------- database packing
+// Builds the paired stream from the plain length-sorted residues: one warp per target pair.
+static __global__ void pack_pairs_kernel(const uint8_t* residues, const long long* offsets, const int* lengths, int numTargets,
+                                  const long long* pairOffsets, int numPairs, uint16_t* pairStream, int* maxCode) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= numPairs) return;
+    const int a = 2 * warp, b = 2 * warp + 1;
+    const uint8_t* sa = residues + offsets[a];
+    const int Ta = lengths[a];
+    const uint8_t* sb = residues;
+    int Tb = 0;
+    if (b < numTargets) { sb = residues + offsets[b]; Tb = lengths[b]; }
+    uint16_t* out = pairStream + pairOffsets[warp];
+    uint32_t mx = 0;
+    for (int c = lane; c < Ta; c += 32) {
+        const uint32_t lo = (uint32_t)sa[c] + 1u;
+        const uint32_t hi = c < Tb ? (uint32_t)sb[c] + 1u : 0u;
+        mx = max(mx, max(lo, hi));
+        out[c] = (uint16_t)(lo | (hi << 8));
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0 && mx > 0) atomicMax(maxCode, (int)mx - 1);  // largest residue code seen
+}
+
 // ------------------------------------------------------------------ DeviceDb
 DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int device) {
     int count = 0;
@@ -340,6 +364,24 @@ DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int
         if (!pinned_alloc((void**)&d->hScore_, nInts)) return false;
         if (!pinned_alloc((void**)&d->hEndQ_, nInts)) return false;
         if (!pinned_alloc((void**)&d->hEndT_, nInts)) return false;
+        // ---- paired stream: [32 zeros][pair 0 columns][32 zeros][pair 1 columns] ... built on the device
+        d->numPairs_ = (n + 1) / 2;
+        std::vector<long long> pairOff((size_t)std::max(d->numPairs_, 1));
+        long long entries = 32;
+        for (int p = 0; p < d->numPairs_; p++) { pairOff[p] = entries; entries += d->sortedLen_[2 * p] + 32; }
+        entries += 64;
+        if (!device_alloc(device, (void**)&d->dPairStream_, sizeof(uint16_t) * (size_t)entries)) return false;
+        if (!device_alloc(device, (void**)&d->dPairOffsets_, sizeof(long long) * pairOff.size())) return false;
+        if (!device_alloc(device, (void**)&d->dMaxCode_, sizeof(int))) return false;
+        CUDA_TRY(cudaMemsetAsync(d->dPairStream_, 0, sizeof(uint16_t) * (size_t)entries, d->stream_));
+        CUDA_TRY(cudaMemsetAsync(d->dMaxCode_, 0, sizeof(int), d->stream_));
+        CUDA_TRY(cudaMemcpyAsync(d->dPairOffsets_, pairOff.data(), sizeof(long long) * pairOff.size(), cudaMemcpyHostToDevice, d->stream_));
+        if (d->numPairs_ > 0) {
+            pack_pairs_kernel<<<(d->numPairs_ + 7) / 8, 256, 0, d->stream_>>>(d->dResidues_, d->dOffsets_, d->dLengths_, n, d->dPairOffsets_,
+                                                                             d->numPairs_, d->dPairStream_, d->dMaxCode_);
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaMemcpyAsync(&d->maxCode_, d->dMaxCode_, sizeof(int), cudaMemcpyDeviceToHost, d->stream_));
         CUDA_TRY(cudaStreamSynchronize(d->stream_));
         pinned_release(staging);
         return true;
@@ -350,7 +392,7 @@ DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int
 DeviceDb::~DeviceDb() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
-    void* dev[] = {dResidues_, dOffsets_, dLengths_, dScore_, dEndQ_, dEndT_, dTaskList_, dCounters_, dBndH_, dBndF_, dQuery_, dMatrix_};
+    void* dev[] = {dResidues_, dOffsets_, dLengths_, dScore_, dEndQ_, dEndT_, dTaskList_, dCounters_, dBndH_, dBndF_, dQuery_, dMatrix_, dPairStream_, dPairOffsets_, dMaxCode_};
     for (void* p : dev) device_release(device_, p);
     pinned_release(hScore_); pinned_release(hEndQ_); pinned_release(hEndT_);
     event_release(device_, evStart_); event_release(device_, evStop_);
@@ -376,10 +418,18 @@ int DeviceDb::run_class(int type, const std::vector<int>& list, const unsigned c
     if (g.passes > 1 && !ensure_boundary()) return OPAL_B200_ERR_CUDA;
     if (*launchSlot + g.passes > 256) { set_error("too many passes"); return OPAL_B200_ERR_CUDA; }
 
-    const bool identity = (int)list.size() == n_;
+    // Packed16 works on the pairs fixed at packing time (targets 2p, 2p+1): a pair runs if either member
+    // is wanted; results of unwanted members are simply not published.
+    std::vector<int> tasks;
+    if (lanes == 2) {
+        for (int t : list) if (tasks.empty() || tasks.back() != (t >> 1)) tasks.push_back(t >> 1);
+    } else {
+        tasks = list;
+    }
+    const bool identity = (int)tasks.size() == (lanes == 2 ? numPairs_ : n_);
     auto okc = [&]() -> bool {
         if (!identity)
-            CUDA_TRY(cudaMemcpyAsync(dTaskList_, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, stream_));
+            CUDA_TRY(cudaMemcpyAsync(dTaskList_, tasks.data(), sizeof(int) * tasks.size(), cudaMemcpyHostToDevice, stream_));
         const int flavor = (mode == kModeSW) ? (wantEnd ? kFlavorSWEnd : kFlavorSWScore) : kFlavorGlobal;
         const void* fn = kernel_tables()[g.tableIndex].fn[type * 3 + flavor];
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
@@ -391,8 +441,9 @@ int DeviceDb::run_class(int type, const std::vector<int>& list, const unsigned c
             p.G = g.G; p.rowBase = pass * g.G * g.R; p.padTop = g.padTop; p.pass = pass; p.numPasses = g.passes;
             p.rowStride = g.rowStride; p.Rpad = g.Rpad;
             p.residues = dResidues_; p.offsets = dOffsets_; p.lengths = dLengths_;
+            p.pairStream = dPairStream_; p.pairOffsets = dPairOffsets_; p.numTargets = n_;
             p.taskList = identity ? nullptr : dTaskList_;
-            p.numTargets = (int)list.size();
+            p.numTasks = (int)tasks.size();
             p.counter = dCounters_ + (*launchSlot)++;
             p.bndH = dBndH_; p.bndF = dBndF_;
             p.outScore = dScore_; p.outEndQ = dEndQ_; p.outEndT = dEndT_;
@@ -400,7 +451,7 @@ int DeviceDb::run_class(int type, const std::vector<int>& list, const unsigned c
             p.padLetterScore = type == 0 ? -16384 : 0;
             void* args[] = {&p};
             const int warpsPerBlock = 4 * g.warpsPerPartition;  // one block per SM, k warps per scheduler partition
-            const long long warpsNeeded = ((long long)list.size() / lanes * g.G + 31) / 32 + 1;
+            const long long warpsNeeded = ((long long)tasks.size() * g.G + 31) / 32;
             const int blocks = (int)std::max<long long>(1, std::min<long long>(numSMs_, (warpsNeeded + warpsPerBlock - 1) / warpsPerBlock));
             CUDA_TRY(cudaLaunchKernel(fn, dim3(blocks), dim3(32 * warpsPerBlock), args, g.smemBytes, stream_));
             stats_.kernelLaunches++;
@@ -417,7 +468,7 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
     stats_ = SearchStats();
     if (deviceMs) *deviceMs = 0.f;
     if (mode != kModeNW && mode != kModeHW && mode != kModeOV && mode != kModeSW) return OPAL_B200_ERR_MODE;
-    if (A <= 0 || A > 255) { set_error("alphabetLength must be in [1, 255]"); return OPAL_B200_ERR_CUDA; }
+    if (A <= 0 || A > 254) { set_error("alphabetLength must be in [1, 254]"); return OPAL_B200_ERR_CUDA; }
     // Argument range of the widest pass (reference src/opal.cpp:183-198, 615-630).
     if (Go <= INT_MIN / 2 || INT_MAX / 2 <= Go || Ge <= INT_MIN / 2 || INT_MAX / 2 <= Ge) return OPAL_B200_ERR_OVERFLOW;
     int maxP = INT_MIN, minP = INT_MAX;
@@ -432,6 +483,10 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
     const bool args16 = absP <= 2048 && gapMax <= 2048;
     const bool args32 = absP < (1 << 28) && gapMax < (1 << 28);
     if (!args32) return OPAL_B200_ERR_OVERFLOW;  // beyond the widths this engine carries (documented deviation)
+
+    if (maxCode_ >= A) { set_error("database holds residue codes >= alphabetLength"); return OPAL_B200_ERR_CUDA; }
+    for (int r = 0; r < Q; r++)
+        if (query[r] >= A) { set_error("query holds residue codes >= alphabetLength"); return OPAL_B200_ERR_CUDA; }
 
     // ---- per-target routing
     const bool isSW = mode == kModeSW;

@@ -69,6 +69,10 @@ private:
     int* dLengths_ = nullptr;
     int *dScore_ = nullptr, *dEndQ_ = nullptr, *dEndT_ = nullptr, *dTaskList_ = nullptr, *dCounters_ = nullptr;
     uint32_t *dBndH_ = nullptr, *dBndF_ = nullptr;
+    uint16_t* dPairStream_ = nullptr;
+    long long* dPairOffsets_ = nullptr;
+    int* dMaxCode_ = nullptr;
+    int numPairs_ = 0, maxCode_ = 0;
     unsigned char* dQuery_ = nullptr;
     int* dMatrix_ = nullptr;
     size_t queryCapacity_ = 0;

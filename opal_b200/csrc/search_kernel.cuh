@@ -49,15 +49,22 @@ struct SearchParams {
     int Q, A, gapOpen, gapExt, mode, wantEnd;
     // geometry of this pass
     int G, rowBase, padTop, pass, numPasses, rowStride, Rpad;
-    // database (length-sorted, concatenated, device resident)
+    // database, device resident, length-sorted (longest first):
+    //   plain:  residues back to back + offsets/lengths per target          (32-bit class, alignment stage)
+    //   paired: targets 2p and 2p+1 interleaved column by column as uint16 = (res0 + 1) | (res1 + 1) << 8,
+    //           0 = "no residue"; every pair is preceded and followed by >= 32 zero entries, so a
+    //           wavefront may read 31 columns before / after a pair without bounds checks
     const uint8_t* residues;
     const long long* offsets;
     const int* lengths;
-    // work: entries of taskList (or 0..numTargets-1 when null) are sorted-target indices
+    const uint16_t* pairStream;
+    const long long* pairOffsets;
+    int numTargets;       // targets in the database (the last pair may have one member)
+    // work: Packed16 tasks are pair indices, Scalar32 tasks are target indices (taskList null = 0..numTasks-1)
     const int* taskList;
-    int numTargets;
+    int numTasks;
     int* counter;
-    // boundary row between passes, indexed by residue offset of the group's first target + column
+    // boundary row between passes, indexed by residue offset of the task's first target + column
     void* bndH;
     void* bndF;
     // running results, indexed by sorted-target index
@@ -67,6 +74,22 @@ struct SearchParams {
     int overflowLimit;  // SW: largest best that is still provably exact at this width
     int padLetterScore; // profile value of the pad letter (before the +gapOpen bias)
 };
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
 // Packed max with per-half "a is still the max" predicates (a >= b).
 // CUDA 12.9's __vibmax_s16x2 (crt/device_functions.hpp:964-983) declares its result "=r" without an
@@ -143,13 +166,14 @@ __device__ __forceinline__ bool better(int s, int c, int r, int S, int C, int R)
 
 // ---------------------------------------------------------------- the kernel
 // Shared memory: plane LO = (A+1) rows x rowStride words, then plane HI likewise (Packed16 only).
-// Word (y, t*Rpad + j) of plane LO holds the biased score of padded query row rowBase + t*R + j
-// against target letter y in its low half-word (sign bits cleared); plane HI holds it shifted
-// left by 16.  Letter A is the "pad letter" used past the end of the shorter target of a pair.
+// Row 0 is the "no residue" letter, row y+1 is target letter y.  Word (row, t*Rpad + j) of plane LO
+// holds the biased score of padded query row rowBase + t*R + j against that letter in its low
+// half-word (sign bits cleared); plane HI holds it shifted left by 16.
 template <int R, int FLAVOR, class TR>
 __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchParams p) {
     typedef typename TR::reg reg;
     constexpr int LANES = TR::LANES;
+    constexpr bool kSW = FLAVOR != kFlavorGlobal;
     extern __shared__ __align__(16) uint32_t smem[];
 
     const int G = p.G, Go = p.gapOpen, Ge = p.gapExt, A = p.A, mode = p.mode;
@@ -157,13 +181,13 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
 
     // ---- build the query profile for this pass
     for (int idx = threadIdx.x; idx < planeWords; idx += blockDim.x) {
-        const int y = idx / p.rowStride, pos = idx - y * p.rowStride;
+        const int row = idx / p.rowStride, pos = idx - row * p.rowStride;
         const int t = pos / p.Rpad, j = pos - t * p.Rpad;
         int sc = Go;  // padding rows score 0 against everything (keeps H = 0 above the query)
         if (t < G && j < R) {
             const int r = p.rowBase + t * R + j - p.padTop;
-            if (r >= 0 && r < p.Q) sc = ((y < A) ? p.matrix[(int)p.query[r] * A + y] : p.padLetterScore) + Go;
-            else if (y == A) sc = p.padLetterScore + Go;
+            if (r >= 0 && r < p.Q) sc = ((row > 0) ? p.matrix[(int)p.query[r] * A + row - 1] : p.padLetterScore) + Go;
+            else if (row == 0) sc = p.padLetterScore + Go;
         }
         if (LANES == 2) {
             smem[idx] = (uint32_t)sc & 0xffffu;
@@ -178,8 +202,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
     const int t = lane & (G - 1);
     const int groupInWarp = lane / G;
     const int groupsPerWarp = 32 / G;
-    const uint32_t* myLo = smem + t * p.Rpad;
-    const uint32_t* myHi = myLo + planeWords;
+    const uint32_t smemBase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t myLo = smemBase + 4u * (uint32_t)(t * p.Rpad);
+    const uint32_t myHi = myLo + 4u * (uint32_t)planeWords;
+    const uint32_t rowBytes = 4u * (uint32_t)p.rowStride;
     const reg negGe = TR::splat(-Ge), negGo = TR::splat(-Go), negGmin = TR::splat(-min(Ge, Go));
     const reg NEGV = TR::splat(TR::NEG);
     const bool firstPass = p.pass == 0, lastPass = p.pass == p.numPasses - 1;
@@ -202,24 +228,29 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
             if (lane == 0) w = totalWarps + atomicAdd(p.counter, 1);
             w = __shfl_sync(0xffffffffu, w, 0);
         }
-        if ((long long)w * groupsPerWarp * LANES >= p.numTargets) break;
+        if ((long long)w * groupsPerWarp >= p.numTasks) break;
 
-        // ---- this group's targets
-        const int i0 = (w * groupsPerWarp + groupInWarp) * LANES;
+        // ---- this group's task: a target pair (Packed16) or one target (Scalar32)
+        const int taskIdx = w * groupsPerWarp + groupInWarp;
         int tgt[2] = {-1, -1}, T[2] = {0, 0};
-        const uint8_t* seq[2] = {p.residues, p.residues};
+        const uint16_t* ps = p.pairStream + 32;  // groups without a task read leading padding only
+        const uint8_t* seq0 = p.residues;
         long long off0 = 0;
-#pragma unroll
-        for (int l = 0; l < LANES; l++) {
-            if (i0 + l < p.numTargets) {
-                tgt[l] = p.taskList ? p.taskList[i0 + l] : i0 + l;
-                T[l] = p.lengths[tgt[l]];
-                const long long o = p.offsets[tgt[l]];
-                seq[l] = p.residues + o;
-                if (l == 0) off0 = o;
+        if (taskIdx < p.numTasks) {
+            const int task = p.taskList ? p.taskList[taskIdx] : taskIdx;
+            if (LANES == 2) {
+                tgt[0] = 2 * task;
+                tgt[1] = (2 * task + 1 < p.numTargets) ? 2 * task + 1 : -1;
+                ps = p.pairStream + p.pairOffsets[task];
+            } else {
+                tgt[0] = task;
             }
+            T[0] = p.lengths[tgt[0]];
+            if (tgt[1] >= 0) T[1] = p.lengths[tgt[1]];
+            off0 = p.offsets[tgt[0]];
+            seq0 = p.residues + off0;
         }
-        const int Tmax = max(T[0], T[1]);
+        const int Tmax = T[0];  // pairs are (longer, shorter)
         const int steps = __reduce_max_sync(0xffffffffu, Tmax > 0 ? Tmax + G - 1 : 0);
 
         // ---- per-thread DP state: column -1
@@ -230,10 +261,10 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
             E[j] = NEGV;
         }
         reg diag = TR::splat(border_h(mode, myRow0 - 1, Go, Ge) - Go);
-        reg outH = NEGV, outF = NEGV;  // bottom of this strip: (H - Go of its last row, F entering the row below)
+        reg outH = kSW ? negGo : NEGV, outF = kSW ? negGo : NEGV;  // bottom of this strip: (H - Go of its last row, F entering the row below)
 
         // tracking state
-        reg best = TR::splat(FLAVOR == kFlavorGlobal ? TR::NEG : 0);  // SW: true H; global: HG of the last row
+        reg best = TR::splat(kSW ? 0 : TR::NEG);                     // SW: true H; global: HG of the last row
         int rowLo = -1, rowHi = -1, colLo = -1, colHi = -1;          // SW end / HW-OV last-row column
         int nwScore[2] = {kScoreNone, kScoreNone};                    // NW final cell
         int lcScore[2] = {kScoreNone, kScoreNone}, lcRow[2] = {-1, -1};  // OV last column
@@ -241,15 +272,20 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
         // boundary prefetch for passes > 0 (thread 0 of the group only)
         const reg* bH = reinterpret_cast<const reg*>(p.bndH) + off0;
         const reg* bF = reinterpret_cast<const reg*>(p.bndF) + off0;
-        reg nextBH = NEGV, nextBF = NEGV;
+        reg nextBH = kSW ? negGo : NEGV, nextBF = nextBH;
         if (!firstPass && t == 0 && Tmax > 0) { nextBH = bH[0]; nextBF = bF[0]; }
-        // residue prefetch
+
+        // residues of column cc as (y0 + 1) | (y1 + 1) << 8, 0 = none.  The paired stream is padded, so
+        // only the upper clamp is needed (a group may idle while longer groups of its warp finish).
+        auto fetch = [&](int cc) -> uint32_t {
+            if (LANES == 2) return ps[min(cc, Tmax)];
+            return (cc >= 0 && cc < Tmax) ? (uint32_t)seq0[cc] + 1u : 0u;
+        };
         int c = -t;
-        int y0n = A, y1n = A;
-        if (c == 0) { if (T[0] > 0) y0n = seq[0][0]; if (LANES == 2 && T[1] > 0) y1n = seq[1][0]; }
+        uint32_t wnext = fetch(c);
 
         for (int s = 0; s < steps; s++, c++) {
-            // ---- (H, F) of the row above, for column c
+            // ---- (H - Go, F) handed down by the row above, for column c
             reg upH = __shfl_up_sync(0xffffffffu, outH, 1, G);
             reg upF = __shfl_up_sync(0xffffffffu, outF, 1, G);
             if (t == 0) {
@@ -259,19 +295,15 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
                 } else {
                     upH = nextBH; upF = nextBF;
                     if (c + 1 < Tmax) { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
+                    else { nextBH = kSW ? negGo : NEGV; nextBF = nextBH; }
                 }
             }
+            const uint32_t wcur = wnext;
+            wnext = fetch(c + 1);
             const bool active = c >= 0 && c < Tmax;
-            const int y0 = y0n, y1 = y1n;
-            {   // prefetch the residues of the next column
-                const int cn = c + 1;
-                y0n = A; y1n = A;
-                if (cn >= 0) {
-                    if (cn < T[0]) y0n = seq[0][cn];
-                    if (LANES == 2 && cn < T[1]) y1n = seq[1][cn];
-                }
-            }
-            if (!active) continue;
+            // SW runs its idle columns too: with the "no residue" letter they leave a state that is
+            // equivalent to the initial one (H = 0, negative E/F never matter) and cannot raise best.
+            if (!kSW && !active) continue;
 
             // ---- one target column for this thread's R query rows.
             // Per cell (Gotoh, reference src/opal.cpp:280-328 / :748-772), with X = max(diag + P, E [, 0]):
@@ -279,27 +311,27 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
             // So the only value carried from row to row is F (one VIADDMNMX per row on the critical
             // path); E, X and X - Go of every row depend on the previous column only.  Row j+1's X is
             // issued before row j's H is written back, which lets H - Go be updated in place.
-            const uint32_t* plo = myLo + y0 * p.rowStride;
-            const uint32_t* phi = myHi + y1 * p.rowStride;
+            const uint32_t plo = myLo + (wcur & 0xffu) * rowBytes;
+            const uint32_t phi = myHi + (wcur >> 8) * rowBytes;
             reg P[R];
             auto load_chunk = [&](int v) {  // rows 4v .. 4v+3 (fewer at the tail): LDS.128 / .64 / .32 per plane
                 const int j0 = v * 4;
                 if (j0 + 4 <= R) {
-                    const uint4 a = *reinterpret_cast<const uint4*>(plo + j0);
+                    const uint4 a = lds128(plo + 4 * j0);
                     uint4 b = a;
-                    if (LANES == 2) b = *reinterpret_cast<const uint4*>(phi + j0);
+                    if (LANES == 2) b = lds128(phi + 4 * j0);
                     P[j0] = TR::combine(a.x, b.x); P[j0 + 1] = TR::combine(a.y, b.y);
                     P[j0 + 2] = TR::combine(a.z, b.z); P[j0 + 3] = TR::combine(a.w, b.w);
                 } else {
                     int j = j0;
                     if (R - j >= 2) {
-                        const uint2 a = *reinterpret_cast<const uint2*>(plo + j);
+                        const uint2 a = lds64(plo + 4 * j);
                         uint2 b = a;
-                        if (LANES == 2) b = *reinterpret_cast<const uint2*>(phi + j);
+                        if (LANES == 2) b = lds64(phi + 4 * j);
                         P[j] = TR::combine(a.x, b.x); P[j + 1] = TR::combine(a.y, b.y);
                         j += 2;
                     }
-                    if (R - j >= 1) P[j] = TR::combine(plo[j], LANES == 2 ? phi[j] : 0u);
+                    if (R - j >= 1) P[j] = TR::combine(lds32(plo + 4 * j), LANES == 2 ? lds32(phi + 4 * j) : 0u);
                 }
             };
             reg f = upF;
@@ -309,7 +341,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
             load_chunk(0);
             reg e0 = TR::addmax(E[0], negGe, HG[0]);
             E[0] = e0;
-            reg X = (FLAVOR == kFlavorGlobal) ? TR::addmax(dIn, P[0], e0) : TR::addmax_relu(dIn, P[0], e0);
+            reg X = kSW ? TR::addmax_relu(dIn, P[0], e0) : TR::addmax(dIn, P[0], e0);
             reg Xprev = 0;
 #pragma unroll
             for (int j = 0; j < R; j++) {
@@ -318,7 +350,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
                     if ((j + 1) % 4 == 0) load_chunk((j + 1) / 4);
                     const reg e1 = TR::addmax(E[j + 1], negGe, HG[j + 1]);
                     E[j + 1] = e1;
-                    Xn = (FLAVOR == kFlavorGlobal) ? TR::addmax(HG[j], P[j + 1], e1) : TR::addmax_relu(HG[j], P[j + 1], e1);
+                    Xn = kSW ? TR::addmax_relu(HG[j], P[j + 1], e1) : TR::addmax(HG[j], P[j + 1], e1);
                 }
                 if (FLAVOR == kFlavorSWScore) {
                     if (j & 1) best = TR::vmax3(best, Xprev, X); else Xprev = X;
@@ -379,7 +411,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
                     }
                 }
             }
-            if (!lastPass && t == G - 1) {
+            if (!lastPass && t == G - 1 && active) {
                 reinterpret_cast<reg*>(p.bndH)[off0 + c] = outH;
                 reinterpret_cast<reg*>(p.bndF)[off0 + c] = outF;
             }
@@ -389,7 +421,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
 #pragma unroll
         for (int l = 0; l < LANES; l++) {
             int sc = kScoreNone, cc = 0x7fffffff, rr = 0x7fffffff;  // this thread's candidate
-            if (FLAVOR != kFlavorGlobal) {
+            if (kSW) {
                 sc = TR::lane(best, l);
                 if (FLAVOR == kFlavorSWEnd && sc > 0) { cc = l ? colHi : colLo; rr = myRow0 + (l ? rowHi : rowLo); }
             } else if (mode == kModeNW) {
@@ -408,21 +440,20 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
             }
             if (t == 0 && tgt[l] >= 0) {
                 const int i = tgt[l];
-                const bool isSW = FLAVOR != kFlavorGlobal;
-                bool overflow = isSW && sc > p.overflowLimit;
+                bool overflow = kSW && sc > p.overflowLimit;
                 if (!firstPass) {
-                    const int ps = p.outScore[i];
-                    if (ps == kScoreOverflow) overflow = true;
-                    else if (ps != kScoreNone && (sc == kScoreNone || better(ps, p.outEndT[i], p.outEndQ[i], sc, cc, rr))) {
-                        sc = ps; cc = p.outEndT[i]; rr = p.outEndQ[i];
+                    const int ps0 = p.outScore[i];
+                    if (ps0 == kScoreOverflow) overflow = true;
+                    else if (ps0 != kScoreNone && (sc == kScoreNone || better(ps0, p.outEndT[i], p.outEndQ[i], sc, cc, rr))) {
+                        sc = ps0; cc = p.outEndT[i]; rr = p.outEndQ[i];
                     }
                 }
                 if (overflow) sc = kScoreOverflow;
                 if (sc != kScoreNone || firstPass) {
                     p.outScore[i] = sc;
-                    const bool haveEnd = p.wantEnd && sc != kScoreOverflow && sc != kScoreNone && !(isSW && sc == 0);
-                    p.outEndT[i] = haveEnd ? cc : (isSW || sc == kScoreNone ? 0x7fffffff : cc);
-                    p.outEndQ[i] = haveEnd ? rr : (isSW || sc == kScoreNone ? 0x7fffffff : rr);
+                    const bool haveEnd = p.wantEnd && sc != kScoreOverflow && sc != kScoreNone && !(kSW && sc == 0);
+                    p.outEndT[i] = haveEnd ? cc : (kSW || sc == kScoreNone ? 0x7fffffff : cc);
+                    p.outEndQ[i] = haveEnd ? rr : (kSW || sc == kScoreNone ? 0x7fffffff : rr);
                 }
             }
         }
