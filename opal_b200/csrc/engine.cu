@@ -181,10 +181,11 @@ static int rpad_of(int R) { const int r4 = (R + 3) / 4; return 4 * ((r4 % 2 == 0
 
 // Picks (G, R, passes, warps per scheduler partition) for a query of Q rows.
 //
-// Timing model (cycles), calibrated against ncu runs (profiles/): the integer pipe retires one packed
-// DPX instruction per 2 cycles per partition, a cell pair costs ~5.5 of them, so a warp's step of R rows
-// takes about 11*R cycles of pipe time plus ~70 cycles of per-step overhead; k warps sharing a partition
-// interleave, so one step of one warp lasts max(k * 11 R, 11 R + 70).  Two bounds follow:
+// Timing model (cycles), calibrated on B200 runs (profiles/): the integer pipe retires one packed DPX
+// instruction per 2 cycles per partition and a cell pair costs ~5.5 of them (11 cycles per row ideal,
+// 14.5 measured with the profile loads and adds around them); a step of one warp alone costs another
+// ~160 cycles of exposed latency (exchange, residue fetch, profile load).  With k warps sharing a
+// partition that latency is hidden, so one step of one warp lasts max(k * 14.5 R, 14.5 R + 160).  Two bounds:
 //   throughput:  sum over warp-tasks of steps * stepTime / (partitions * k)
 //   tail:        the longest target's steps * stepTime  (it cannot be split across warps)
 // Small databases with a long tail (BASELINE configs[1]) are tail-bound and want G = 32 and k = 1;
@@ -215,7 +216,7 @@ static bool pick_geometry(int Q, int A, int lanes, const std::vector<int>& lens,
             for (int k = 1; k <= 4; k *= 2) {
                 // with fewer warp-tasks than resident warps the partitions are not shared k ways
                 const double kEff = std::max(1.0, std::min((double)k, std::ceil(warpTasks / (numSMs * 4.0))));
-                const double stepTime = std::max(kEff * 11.0 * R, 11.0 * R + 70.0);
+                const double stepTime = std::max(kEff * 14.5 * R, 14.5 * R + 160.0);
                 const double warpsBusy = std::min((double)numSMs * 4 * k, warpTasks);
                 const double throughput = warpSteps * stepTime / warpsBusy;
                 const double tail = (maxLen + G - 1) * stepTime;
@@ -430,8 +431,14 @@ int DeviceDb::run_class(int type, const std::vector<int>& list, const unsigned c
     auto okc = [&]() -> bool {
         if (!identity)
             CUDA_TRY(cudaMemcpyAsync(dTaskList_, tasks.data(), sizeof(int) * tasks.size(), cudaMemcpyHostToDevice, stream_));
-        const int flavor = (mode == kModeSW) ? (wantEnd ? kFlavorSWEnd : kFlavorSWScore) : kFlavorGlobal;
-        const void* fn = kernel_tables()[g.tableIndex].fn[type * 3 + flavor];
+        // SW score+end at 16 bits first tries the key-tracking flavor (exact below fastEndLimit; the rest is
+        // flagged like an overflow and re-run exactly at 32 bits).
+        const int fastEndLimit = (32768 >> kRowBits) - std::max(maxScore, 0) - 1;
+        // It pays in the throughput regime (>= 2 warps per partition); tail-bound searches go exact at once.
+        const bool fastEnd = mode == kModeSW && wantEnd && type == 0 && g.R <= (1 << kRowBits) && fastEndLimit >= 64 &&
+                             g.warpsPerPartition >= 2 && !getenv("OPAL_B200_EXACT_END");
+        const int flavor = (mode == kModeSW) ? (wantEnd ? (fastEnd ? kFlavorSWEndFast : kFlavorSWEnd) : kFlavorSWScore) : kFlavorGlobal;
+        const void* fn = kernel_tables()[g.tableIndex].fn[type * 4 + flavor];
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
         for (int pass = 0; pass < g.passes; pass++) {
             SearchParams p;
@@ -449,6 +456,7 @@ int DeviceDb::run_class(int type, const std::vector<int>& list, const unsigned c
             p.outScore = dScore_; p.outEndQ = dEndQ_; p.outEndT = dEndT_;
             p.overflowLimit = type == 0 ? 32767 - std::max(maxScore, 0) - 1 : (1 << 30);
             p.padLetterScore = type == 0 ? -16384 : 0;
+            p.one = 1; p.keyScale = 1 << kRowBits; p.fastEndLimit = fastEndLimit;
             void* args[] = {&p};
             const int warpsPerBlock = 4 * g.warpsPerPartition;  // one block per SM, k warps per scheduler partition
             const long long warpsNeeded = ((long long)tasks.size() * g.G + 31) / 32;

@@ -12,7 +12,7 @@ namespace opalb200 {
 constexpr int OPAL_B200_ERR_OVERFLOW = 1, OPAL_B200_ERR_CUDA = 2, OPAL_B200_ERR_MODE = 3;
 
 // Kernel registry: one translation unit per strip height R (kernels_inst.cu compiled with
-// -DOPAL_R=<R>), each exporting a table indexed [type * 3 + flavor]; type 0 = Packed16, 1 = Scalar32.
+// -DOPAL_R=<R>), each exporting a table indexed [type * 4 + flavor]; type 0 = Packed16, 1 = Scalar32.
 struct KernelTable {
     int R;
     const void* const* fn;

@@ -8,13 +8,15 @@
 #define OPAL_CAT(a, b) OPAL_CAT2(a, b)
 
 namespace opalb200 {
-static const void* const kTable[6] = {
+static const void* const kTable[8] = {
     (const void*)search_kernel<OPAL_R, kFlavorSWScore, Packed16>,
     (const void*)search_kernel<OPAL_R, kFlavorSWEnd, Packed16>,
     (const void*)search_kernel<OPAL_R, kFlavorGlobal, Packed16>,
+    (const void*)search_kernel<OPAL_R, kFlavorSWEndFast, Packed16>,
     (const void*)search_kernel<OPAL_R, kFlavorSWScore, Scalar32>,
     (const void*)search_kernel<OPAL_R, kFlavorSWEnd, Scalar32>,
     (const void*)search_kernel<OPAL_R, kFlavorGlobal, Scalar32>,
+    (const void*)search_kernel<OPAL_R, kFlavorSWEnd, Scalar32>,  // no fast variant at 32 bits
 };
 const void* const* OPAL_CAT(kernel_table_R, OPAL_R)() { return kTable; }
 }  // namespace opalb200

@@ -38,7 +38,8 @@ namespace opalb200 {
 
 constexpr int kBlockThreads = 512;
 constexpr int kModeNW = 0, kModeHW = 1, kModeOV = 2, kModeSW = 3;
-constexpr int kFlavorSWScore = 0, kFlavorSWEnd = 1, kFlavorGlobal = 2;
+constexpr int kFlavorSWScore = 0, kFlavorSWEnd = 1, kFlavorGlobal = 2, kFlavorSWEndFast = 3;
+constexpr int kRowBits = 6;  // kFlavorSWEndFast: low bits of the tracked key hold 63 - row
 constexpr int kScoreNone = INT32_MIN;          // "no candidate yet" in the running-result arrays
 constexpr int kScoreOverflow = INT32_MIN + 1;  // 16-bit pass: re-run this target in 32 bits
 
@@ -73,6 +74,9 @@ struct SearchParams {
     int* outEndT;
     int overflowLimit;  // SW: largest best that is still provably exact at this width
     int padLetterScore; // profile value of the pad letter (before the +gapOpen bias)
+    int one;            // the constant 1, opaque to the compiler (see vimax_track_s16x2)
+    int keyScale;       // 1 << kRowBits, opaque to the compiler so that the key is built by an IMAD (FMA pipe)
+    int fastEndLimit;   // kFlavorSWEndFast: tracked scores at or above this are re-run by the exact flavor
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -117,6 +121,27 @@ __device__ __forceinline__ uint32_t vibmax_s16x2(uint32_t a, uint32_t b, bool* p
     return val;
 }
 
+// best = max(best, x) per half-word; where a half strictly improves, its row register takes `row`.
+// One VIMNMX.S16x2 with two predicate outputs plus two predicated IMADs: `one` is a run-time 1, so the
+// row update is a multiply on the FMA pipe instead of a SEL competing with the DPX work on the integer pipe.
+__device__ __forceinline__ uint32_t vimax_track_s16x2(uint32_t best, uint32_t x, int& rowLo, int& rowHi, int row, int one) {
+    uint32_t val;
+    asm("{.reg .pred pu, pv;\n\t"
+        ".reg .s16 rs0, rs1, rs2, rs3;\n\t"
+        ".reg .b32 t;\n\t"
+        "max.s16x2 t, %3, %4;\n\t"
+        "mov.b32 {rs0, rs1}, t;\n\t"
+        "mov.b32 {rs2, rs3}, %3;\n\t"
+        "setp.eq.s16 pv, rs0, rs2;\n\t"
+        "setp.eq.s16 pu, rs1, rs3;\n\t"
+        "@!pv mul.lo.s32 %1, %6, %5;\n\t"
+        "@!pu mul.lo.s32 %2, %6, %5;\n\t"
+        "mov.b32 %0, t;}\n\t"
+        : "=&r"(val), "+r"(rowLo), "+r"(rowHi)
+        : "r"(best), "r"(x), "r"(row), "r"(one));
+    return val;
+}
+
 // ---------------------------------------------------------------- arithmetic traits
 struct Packed16 {
     typedef uint32_t reg;
@@ -131,6 +156,7 @@ struct Packed16 {
     static __device__ __forceinline__ reg vmax3(reg a, reg b, reg c) { return __vimax3_s16x2(a, b, c); }
     static __device__ __forceinline__ reg add(reg a, reg b) { return __vadd2(a, b); }
     static __device__ __forceinline__ reg bmax(reg a, reg b, bool* phi, bool* plo) { return vibmax_s16x2(a, b, phi, plo); }
+    static __device__ __forceinline__ reg track(reg best, reg x, int& rowLo, int& rowHi, int row, int one) { return vimax_track_s16x2(best, x, rowLo, rowHi, row, one); }
     static __device__ __forceinline__ reg combine(uint32_t lo, uint32_t hi) { return lo + hi; }
 };
 
@@ -147,6 +173,12 @@ struct Scalar32 {
     static __device__ __forceinline__ reg vmax3(reg a, reg b, reg c) { return __vimax3_s32(a, b, c); }
     static __device__ __forceinline__ reg add(reg a, reg b) { return a + b; }
     static __device__ __forceinline__ reg bmax(reg a, reg b, bool* phi, bool* plo) { *phi = true; return __vibmax_s32(a, b, plo); }
+    static __device__ __forceinline__ reg track(reg best, reg x, int& rowLo, int&, int row, int) {
+        bool keep;
+        const reg v = __vibmax_s32(best, x, &keep);
+        if (!keep) rowLo = row;
+        return v;
+    }
     static __device__ __forceinline__ reg combine(uint32_t lo, uint32_t) { return (int)lo; }
 };
 
@@ -208,6 +240,31 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
     const uint32_t rowBytes = 4u * (uint32_t)p.rowStride;
     const reg negGe = TR::splat(-Ge), negGo = TR::splat(-Go), negGmin = TR::splat(-min(Ge, Go));
     const reg NEGV = TR::splat(TR::NEG);
+    // Keeping P[] live across steps and reloading each chunk for the next column right after its use was
+    // measured slower on B200 (0.83 vs 0.75 ms on BASELINE configs[1]: extra registers, no shorter step) and
+    // is incompatible with skipped idle columns, so it stays off; the code path is kept for re-evaluation.
+    constexpr bool kPrefetchP = false;
+    // rows 4v .. 4v+3 (fewer at the tail) of one profile column: LDS.128 / .64 / .32 per plane
+    auto load_chunk = [&](reg* P, uint32_t plo, uint32_t phi, int v) {
+        const int j0 = v * 4;
+        if (j0 + 4 <= R) {
+            const uint4 a = lds128(plo + 4 * j0);
+            uint4 b = a;
+            if (LANES == 2) b = lds128(phi + 4 * j0);
+            P[j0] = TR::combine(a.x, b.x); P[j0 + 1] = TR::combine(a.y, b.y);
+            P[j0 + 2] = TR::combine(a.z, b.z); P[j0 + 3] = TR::combine(a.w, b.w);
+        } else {
+            int j = j0;
+            if (R - j >= 2) {
+                const uint2 a = lds64(plo + 4 * j);
+                uint2 b = a;
+                if (LANES == 2) b = lds64(phi + 4 * j);
+                P[j] = TR::combine(a.x, b.x); P[j + 1] = TR::combine(a.y, b.y);
+                j += 2;
+            }
+            if (R - j >= 1) P[j] = TR::combine(lds32(plo + 4 * j), LANES == 2 ? lds32(phi + 4 * j) : 0u);
+        }
+    };
     const bool firstPass = p.pass == 0, lastPass = p.pass == p.numPasses - 1;
     const int myRow0 = p.rowBase + t * R - p.padTop;  // query row of this thread's register 0
     // NW keeps padding at the bottom, so its last query row sits at a run-time position.
@@ -264,7 +321,8 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
         reg outH = kSW ? negGo : NEGV, outF = kSW ? negGo : NEGV;  // bottom of this strip: (H - Go of its last row, F entering the row below)
 
         // tracking state
-        reg best = TR::splat(kSW ? 0 : TR::NEG);                     // SW: true H; global: HG of the last row
+        // SW: running max of H (kFlavorSWEndFast: of the key H << 6 | 63 - row, see below); global: H - Go of the last row
+        reg best = TR::splat(FLAVOR == kFlavorSWEndFast ? (1 << kRowBits) - 1 : (kSW ? 0 : TR::NEG));
         int rowLo = -1, rowHi = -1, colLo = -1, colHi = -1;          // SW end / HW-OV last-row column
         int nwScore[2] = {kScoreNone, kScoreNone};                    // NW final cell
         int lcScore[2] = {kScoreNone, kScoreNone}, lcRow[2] = {-1, -1};  // OV last column
@@ -283,20 +341,31 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
         };
         int c = -t;
         uint32_t wnext = fetch(c);
+        reg P[R];
+        if (kPrefetchP) {
+            const uint32_t plo0 = myLo + (wnext & 0xffu) * rowBytes, phi0 = myHi + (wnext >> 8) * rowBytes;
+#pragma unroll
+            for (int v = 0; v < (R + 3) / 4; v++) load_chunk(P, plo0, phi0, v);
+        }
 
         for (int s = 0; s < steps; s++, c++) {
             // ---- (H - Go, F) handed down by the row above, for column c
             reg upH = __shfl_up_sync(0xffffffffu, outH, 1, G);
             reg upF = __shfl_up_sync(0xffffffffu, outF, 1, G);
-            if (t == 0) {
+            {   // thread 0 has no thread above: row -1 of the matrix (first pass) or the previous pass's
+                // boundary row.  Written as selects / predicated loads: a per-step divergent branch here
+                // costs more than the whole exchange.
+                reg synH, synF;
                 if (firstPass) {
-                    upH = TR::splat((mode == kModeNW ? -Go - c * Ge : 0) - Go);  // row -1, reference :716-732
-                    upF = upH;  // F entering row 0 = max(-inf - Ge, H[-1][c] - Go)
+                    synH = TR::splat((mode == kModeNW ? -Go - c * Ge : 0) - Go);  // row -1, reference :716-732
+                    synF = synH;  // F entering row 0 = max(-inf - Ge, H[-1][c] - Go)
                 } else {
-                    upH = nextBH; upF = nextBF;
-                    if (c + 1 < Tmax) { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
-                    else { nextBH = kSW ? negGo : NEGV; nextBF = nextBH; }
+                    synH = nextBH; synF = nextBF;
+                    nextBH = kSW ? negGo : NEGV; nextBF = nextBH;
+                    if (t == 0 && c + 1 < Tmax) { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
                 }
+                upH = (t == 0) ? synH : upH;
+                upF = (t == 0) ? synF : upF;
             }
             const uint32_t wcur = wnext;
             wnext = fetch(c + 1);
@@ -311,54 +380,43 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
             // So the only value carried from row to row is F (one VIADDMNMX per row on the critical
             // path); E, X and X - Go of every row depend on the previous column only.  Row j+1's X is
             // issued before row j's H is written back, which lets H - Go be updated in place.
-            const uint32_t plo = myLo + (wcur & 0xffu) * rowBytes;
-            const uint32_t phi = myHi + (wcur >> 8) * rowBytes;
-            reg P[R];
-            auto load_chunk = [&](int v) {  // rows 4v .. 4v+3 (fewer at the tail): LDS.128 / .64 / .32 per plane
-                const int j0 = v * 4;
-                if (j0 + 4 <= R) {
-                    const uint4 a = lds128(plo + 4 * j0);
-                    uint4 b = a;
-                    if (LANES == 2) b = lds128(phi + 4 * j0);
-                    P[j0] = TR::combine(a.x, b.x); P[j0 + 1] = TR::combine(a.y, b.y);
-                    P[j0 + 2] = TR::combine(a.z, b.z); P[j0 + 3] = TR::combine(a.w, b.w);
-                } else {
-                    int j = j0;
-                    if (R - j >= 2) {
-                        const uint2 a = lds64(plo + 4 * j);
-                        uint2 b = a;
-                        if (LANES == 2) b = lds64(phi + 4 * j);
-                        P[j] = TR::combine(a.x, b.x); P[j + 1] = TR::combine(a.y, b.y);
-                        j += 2;
-                    }
-                    if (R - j >= 1) P[j] = TR::combine(lds32(plo + 4 * j), LANES == 2 ? lds32(phi + 4 * j) : 0u);
-                }
+            // Profile values of this column.  Short strips (R <= 20) keep P[] live across steps and reload each
+            // 4-row chunk for the NEXT column as soon as it has been consumed, which takes the shared-memory
+            // latency off the critical path of a warp that runs alone on its scheduler partition.
+            const uint32_t plo = myLo + (wcur & 0xffu) * rowBytes, phi = myHi + (wcur >> 8) * rowBytes;
+            const uint32_t ploNext = myLo + (wnext & 0xffu) * rowBytes, phiNext = myHi + (wnext >> 8) * rowBytes;
+            if (!kPrefetchP) load_chunk(P, plo, phi, 0);
+            auto consumed = [&](int row) {  // P[row] has just been used
+                if (kPrefetchP) { if (row % 4 == 3 || row == R - 1) load_chunk(P, ploNext, phiNext, row / 4); }
+                else if (row % 4 == 3 && row + 1 < R) load_chunk(P, plo, phi, row / 4 + 1);
             };
             reg f = upF;
             const reg dIn = diag;
             diag = upH;
             const reg bestBefore = best;
-            load_chunk(0);
             reg e0 = TR::addmax(E[0], negGe, HG[0]);
             E[0] = e0;
             reg X = kSW ? TR::addmax_relu(dIn, P[0], e0) : TR::addmax(dIn, P[0], e0);
+            consumed(0);
             reg Xprev = 0;
 #pragma unroll
             for (int j = 0; j < R; j++) {
                 reg Xn = 0;
                 if (j + 1 < R) {
-                    if ((j + 1) % 4 == 0) load_chunk((j + 1) / 4);
                     const reg e1 = TR::addmax(E[j + 1], negGe, HG[j + 1]);
                     E[j + 1] = e1;
                     Xn = kSW ? TR::addmax_relu(HG[j], P[j + 1], e1) : TR::addmax(HG[j], P[j + 1], e1);
                 }
+                if (j + 1 < R) consumed(j + 1);
                 if (FLAVOR == kFlavorSWScore) {
                     if (j & 1) best = TR::vmax3(best, Xprev, X); else Xprev = X;
                 } else if (FLAVOR == kFlavorSWEnd) {
-                    bool ph, pl;
-                    best = TR::bmax(best, X, &ph, &pl);
-                    if (!pl) rowLo = j;
-                    if (LANES == 2 && !ph) rowHi = j;
+                    best = TR::track(best, X, rowLo, rowHi, j, p.one);
+                } else if (FLAVOR == kFlavorSWEndFast) {
+                    // key = H << 6 | (63 - row) in both half-words: one IMAD (FMA pipe) and one VIMNMX.  Exact while
+                    // H < 512; larger scores are detected at the end (fastEndLimit) and re-run by kFlavorSWEnd.
+                    const uint32_t rowBits = (uint32_t)((1 << kRowBits) - 1 - j) * 0x00010001u;
+                    best = TR::vmax(best, (reg)((uint32_t)X * (uint32_t)p.keyScale + rowBits));
                 }
                 const reg XG = TR::add(X, negGo);
                 HG[j] = TR::addmax(f, negGo, XG);   // H - Go = max(X, F) - Go
@@ -373,6 +431,15 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
                 const reg ch = best ^ bestBefore;
                 if (LANES == 2) { if (ch & 0xffffu) colLo = c; if (ch >> 16) colHi = c; }
                 else if (ch) colLo = c;
+            }
+            if (FLAVOR == kFlavorSWEndFast) {
+                // A changed half-word means a strictly larger (score, first row) in THIS column: latch row and
+                // column, then saturate the row bits so that equal scores of later columns cannot win.
+                const uint32_t b = (uint32_t)best, ch = b ^ (uint32_t)bestBefore;
+                const int mask = (1 << kRowBits) - 1;
+                if (ch & 0xffffu) { colLo = c; rowLo = mask - (int)(b & mask); }
+                if (ch >> 16) { colHi = c; rowHi = mask - (int)((b >> 16) & mask); }
+                best = (reg)(b | (uint32_t)mask * 0x00010001u);
             }
             if (FLAVOR == kFlavorGlobal) {
                 if (mode == kModeNW) {
@@ -418,12 +485,14 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
         }
 
         // ---- reduce the group's candidates and merge them into the running results
+        int fsc[2], fcc[2], frr[2];
 #pragma unroll
         for (int l = 0; l < LANES; l++) {
             int sc = kScoreNone, cc = 0x7fffffff, rr = 0x7fffffff;  // this thread's candidate
             if (kSW) {
                 sc = TR::lane(best, l);
-                if (FLAVOR == kFlavorSWEnd && sc > 0) { cc = l ? colHi : colLo; rr = myRow0 + (l ? rowHi : rowLo); }
+                if (FLAVOR == kFlavorSWEndFast) sc >>= kRowBits;
+                if ((FLAVOR == kFlavorSWEnd || FLAVOR == kFlavorSWEndFast) && sc > 0) { cc = l ? colHi : colLo; rr = myRow0 + (l ? rowHi : rowLo); }
             } else if (mode == kModeNW) {
                 sc = nwScore[l]; cc = T[l] - 1; rr = p.Q - 1;
             } else {
@@ -438,9 +507,21 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
                 const int r2 = __shfl_xor_sync(0xffffffffu, rr, o);
                 if (better(s2, c2, r2, sc, cc, rr)) { sc = s2; cc = c2; rr = r2; }
             }
+            fsc[l] = sc; fcc[l] = cc; frr[l] = rr;
+        }
+        // kFlavorSWEndFast: a half-word whose score left the exact range may also have spilled into its
+        // neighbour, so the whole pair is handed to the exact flavor.
+        bool pairInexact = false;
+        if (FLAVOR == kFlavorSWEndFast) {
+#pragma unroll
+            for (int l = 0; l < LANES; l++) pairInexact |= fsc[l] >= p.fastEndLimit;
+        }
+#pragma unroll
+        for (int l = 0; l < LANES; l++) {
             if (t == 0 && tgt[l] >= 0) {
                 const int i = tgt[l];
-                bool overflow = kSW && sc > p.overflowLimit;
+                int sc = fsc[l], cc = fcc[l], rr = frr[l];
+                bool overflow = (kSW && sc > p.overflowLimit) || pairInexact;
                 if (!firstPass) {
                     const int ps0 = p.outScore[i];
                     if (ps0 == kScoreOverflow) overflow = true;
