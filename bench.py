@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from opal_b200 import (MODES, OPAL_OVERFLOW_BUCKETS, OPAL_SEARCH_SCORE_END, OpalCLibrary, SequenceDB,  # noqa: E402
-                       datasets, matrices, new_results)
+                       datasets, matrices, new_results, sharding)
 
 GAP_OPEN, GAP_EXT = 11, 1
 MODE = "SW"
@@ -47,10 +47,7 @@ def make_workload(name, rank, world):
         scaling = "weak"
     elif name == "config3":
         full = datasets.config3_db(sm, query=query)
-        order = np.argsort(-full.lengths, kind="stable")
-        mine = order[rank::world]  # deal length-sorted sequences round-robin: residue-balanced shards
-        db = SequenceDB(np.concatenate([full.sequence(int(i)) for i in mine]),
-                        np.concatenate([[0], np.cumsum(full.lengths[mine])])) if world > 1 else full
+        db = sharding.shard_db(full, sharding.deal_shards(full.lengths, world)[rank]) if world > 1 else full
         desc = ("BASELINE configs[2] DB: 570k seqs / ~206M residues, Swiss-Prot-shaped with heavy tail, "
                 "SW score+end, P18080 (Q=513), BLOSUM62 11/1; DB dealt residue-balanced over the GPUs")
         scaling = "strong"

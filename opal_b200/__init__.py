@@ -11,3 +11,4 @@ from .capi import (  # noqa: F401
     OPAL_MODE_SW, OPAL_OVERFLOW_BUCKETS, OPAL_OVERFLOW_SIMPLE, OPAL_SEARCH_ALIGNMENT,
     OPAL_SEARCH_SCORE, OPAL_SEARCH_SCORE_END, MODES, OpalCLibrary, SequenceDB, free_alignments,
     get_alignment, new_results)
+from . import sharding  # noqa: F401,E402
