@@ -213,7 +213,7 @@ static bool pick_geometry(int Q, int A, int lanes, const std::vector<int>& lens,
             const double groupsPerWarp = 32.0 / G;
             const double warpSteps = (sumLen + tasks * (G - 1)) / groupsPerWarp;  // per pass
             const double warpTasks = std::max(1.0, tasks / groupsPerWarp);
-            for (int k = 1; k <= 4; k *= 2) {
+            for (int k = 1; k <= kBlockThreads / 128; k *= 2) {
                 // with fewer warp-tasks than resident warps the partitions are not shared k ways
                 const double kEff = std::max(1.0, std::min((double)k, std::ceil(warpTasks / (numSMs * 4.0))));
                 const double stepTime = std::max(kEff * 14.5 * R, 14.5 * R + 160.0);
@@ -234,7 +234,7 @@ static bool pick_geometry(int Q, int A, int lanes, const std::vector<int>& lens,
     // Development override: OPAL_B200_GEOMETRY="G,R,k" forces a geometry (ignored when it does not fit).
     if (const char* env = getenv("OPAL_B200_GEOMETRY")) {
         int G = 0, R = 0, k = 0;
-        if (sscanf(env, "%d,%d,%d", &G, &R, &k) == 3 && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && k >= 1 && k <= 4) {
+        if (sscanf(env, "%d,%d,%d", &G, &R, &k) == 3 && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && k >= 1 && k <= kBlockThreads / 128) {
             for (size_t ti = 0; ti < tables.size(); ti++) {
                 if (tables[ti].R != R) continue;
                 const int Rpad = rpad_of(R), rowStride = (G * Rpad + 31) / 32 * 32;
@@ -402,7 +402,7 @@ DeviceDb::~DeviceDb() {
 
 bool DeviceDb::ensure_boundary() {
     if (dBndH_) return true;
-    const size_t bytes = sizeof(uint32_t) * (size_t)(totalResidues_ + 64);
+    const size_t bytes = 2 * sizeof(uint32_t) * (size_t)(totalResidues_ + 64);  // two halves: ping-pong between passes
     if (!device_alloc(device_, (void**)&dBndH_, bytes) || !device_alloc(device_, (void**)&dBndF_, bytes)) return false;
     return true;
 }
@@ -431,12 +431,11 @@ int DeviceDb::run_class(int type, const std::vector<int>& list, const unsigned c
     auto okc = [&]() -> bool {
         if (!identity)
             CUDA_TRY(cudaMemcpyAsync(dTaskList_, tasks.data(), sizeof(int) * tasks.size(), cudaMemcpyHostToDevice, stream_));
-        // SW score+end at 16 bits first tries the key-tracking flavor (exact below fastEndLimit; the rest is
-        // flagged like an overflow and re-run exactly at 32 bits).
+        // SW score+end at 16 bits uses the key-tracking flavor: exact below fastEndLimit, and warps that meet a
+        // larger score sweep their tasks again with the exact per-cell tracking inside the same kernel.
         const int fastEndLimit = (32768 >> kRowBits) - std::max(maxScore, 0) - 1;
-        // It pays in the throughput regime (>= 2 warps per partition); tail-bound searches go exact at once.
         const bool fastEnd = mode == kModeSW && wantEnd && type == 0 && g.R <= (1 << kRowBits) && fastEndLimit >= 64 &&
-                             g.warpsPerPartition >= 2 && !getenv("OPAL_B200_EXACT_END");
+                             !getenv("OPAL_B200_EXACT_END");
         const int flavor = (mode == kModeSW) ? (wantEnd ? (fastEnd ? kFlavorSWEndFast : kFlavorSWEnd) : kFlavorSWScore) : kFlavorGlobal;
         const void* fn = kernel_tables()[g.tableIndex].fn[type * 4 + flavor];
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
@@ -452,7 +451,9 @@ int DeviceDb::run_class(int type, const std::vector<int>& list, const unsigned c
             p.taskList = identity ? nullptr : dTaskList_;
             p.numTasks = (int)tasks.size();
             p.counter = dCounters_ + (*launchSlot)++;
-            p.bndH = dBndH_; p.bndF = dBndF_;
+            const size_t half = (size_t)(totalResidues_ + 64);
+            p.bndInH = dBndH_ ? dBndH_ + ((pass + 1) & 1) * half : nullptr; p.bndInF = dBndF_ ? dBndF_ + ((pass + 1) & 1) * half : nullptr;
+            p.bndOutH = dBndH_ ? dBndH_ + (pass & 1) * half : nullptr; p.bndOutF = dBndF_ ? dBndF_ + (pass & 1) * half : nullptr;
             p.outScore = dScore_; p.outEndQ = dEndQ_; p.outEndT = dEndT_;
             p.overflowLimit = type == 0 ? 32767 - std::max(maxScore, 0) - 1 : (1 << 30);
             p.padLetterScore = type == 0 ? -16384 : 0;
@@ -607,13 +608,13 @@ double measure_dpx_peak(int device, double* threadInstrPerSec, float* msOut) {
     cudaGetDeviceProperties(&prop, device);
     const int blocks = prop.multiProcessorCount * 2;
     uint32_t* out = nullptr;
-    if (cudaMalloc(&out, sizeof(uint32_t) * blocks * kBlockThreads) != cudaSuccess) { set_error("cudaMalloc failed"); return 0.0; }
+    if (cudaMalloc(&out, sizeof(uint32_t) * blocks * 512) != cudaSuccess) { set_error("cudaMalloc failed"); return 0.0; }
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     float best = 1e30f;
     for (int rep = 0; rep < 5; rep++) {
         cudaEventRecord(a);
-        dpx_peak_kernel<ILP><<<blocks, kBlockThreads>>>(out, iters, 12345u + rep);
+        dpx_peak_kernel<ILP><<<blocks, 512>>>(out, iters, 12345u + rep);
         cudaEventRecord(b);
         cudaEventSynchronize(b);
         float ms = 0;
@@ -623,7 +624,7 @@ double measure_dpx_peak(int device, double* threadInstrPerSec, float* msOut) {
     const cudaError_t e = cudaGetLastError();
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return 0.0; }
-    const double instr = 6.0 * ILP * (double)iters * blocks * kBlockThreads;  // thread-level packed instructions
+    const double instr = 6.0 * ILP * (double)iters * blocks * 512;  // thread-level packed instructions
     const double ips = instr / (best * 1e-3);
     if (threadInstrPerSec) *threadInstrPerSec = ips;
     if (msOut) *msOut = best;

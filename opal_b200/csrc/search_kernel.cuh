@@ -34,9 +34,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace opalb200 {
 
-constexpr int kBlockThreads = 512;
+constexpr int kBlockThreads = 256;  // at most 2 warps per scheduler partition: measured as fast as 4, and leaves 255 registers per thread
 constexpr int kModeNW = 0, kModeHW = 1, kModeOV = 2, kModeSW = 3;
 constexpr int kFlavorSWScore = 0, kFlavorSWEnd = 1, kFlavorGlobal = 2, kFlavorSWEndFast = 3;
 constexpr int kRowBits = 6;  // kFlavorSWEndFast: low bits of the tracked key hold 63 - row
@@ -65,9 +67,13 @@ struct SearchParams {
     const int* taskList;
     int numTasks;
     int* counter;
-    // boundary row between passes, indexed by residue offset of the task's first target + column
-    void* bndH;
-    void* bndF;
+    // boundary row between passes, indexed by residue offset of the task's first target + column; a pass
+    // reads the previous pass's rows from bndIn* and writes its own to bndOut* (ping-pong, so that a warp may
+    // sweep a task twice)
+    const void* bndInH;
+    const void* bndInF;
+    void* bndOutH;
+    void* bndOutF;
     // running results, indexed by sorted-target index
     int* outScore;
     int* outEndQ;
@@ -310,28 +316,30 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
         const int Tmax = T[0];  // pairs are (longer, shorter)
         const int steps = __reduce_max_sync(0xffffffffu, Tmax > 0 ? Tmax + G - 1 : 0);
 
-        // ---- per-thread DP state: column -1
+        // ---- per-thread DP state and tracking state; (re)initialised by init_state() to column -1
         reg HG[R], E[R];
+        reg diag, outH, outF;  // outH/outF: bottom of this strip = (H - Go of its last row, F entering the row below)
+        reg best;              // SW: running max of H (fast flavor: of the key H << 6 | 63 - row); global: H - Go of the last row
+        int rowLo, rowHi, colLo, colHi;          // SW end / HW-OV last-row column
+        int nwScore[2], lcScore[2], lcRow[2];    // NW final cell; OV last column
+        const reg* bH = reinterpret_cast<const reg*>(p.bndInH) + off0;  // boundary rows of the previous pass
+        const reg* bF = reinterpret_cast<const reg*>(p.bndInF) + off0;
+        reg nextBH, nextBF;
+        auto init_state = [&](bool keyTracking) {
 #pragma unroll
-        for (int j = 0; j < R; j++) {
-            HG[j] = TR::splat(border_h(mode, myRow0 + j, Go, Ge) - Go);
-            E[j] = NEGV;
-        }
-        reg diag = TR::splat(border_h(mode, myRow0 - 1, Go, Ge) - Go);
-        reg outH = kSW ? negGo : NEGV, outF = kSW ? negGo : NEGV;  // bottom of this strip: (H - Go of its last row, F entering the row below)
-
-        // tracking state
-        // SW: running max of H (kFlavorSWEndFast: of the key H << 6 | 63 - row, see below); global: H - Go of the last row
-        reg best = TR::splat(FLAVOR == kFlavorSWEndFast ? (1 << kRowBits) - 1 : (kSW ? 0 : TR::NEG));
-        int rowLo = -1, rowHi = -1, colLo = -1, colHi = -1;          // SW end / HW-OV last-row column
-        int nwScore[2] = {kScoreNone, kScoreNone};                    // NW final cell
-        int lcScore[2] = {kScoreNone, kScoreNone}, lcRow[2] = {-1, -1};  // OV last column
-
-        // boundary prefetch for passes > 0 (thread 0 of the group only)
-        const reg* bH = reinterpret_cast<const reg*>(p.bndH) + off0;
-        const reg* bF = reinterpret_cast<const reg*>(p.bndF) + off0;
-        reg nextBH = kSW ? negGo : NEGV, nextBF = nextBH;
-        if (!firstPass && t == 0 && Tmax > 0) { nextBH = bH[0]; nextBF = bF[0]; }
+            for (int j = 0; j < R; j++) {
+                HG[j] = TR::splat(border_h(mode, myRow0 + j, Go, Ge) - Go);
+                E[j] = NEGV;
+            }
+            diag = TR::splat(border_h(mode, myRow0 - 1, Go, Ge) - Go);
+            outH = kSW ? negGo : NEGV; outF = outH;
+            best = TR::splat(keyTracking ? (1 << kRowBits) - 1 : (kSW ? 0 : TR::NEG));
+            rowLo = rowHi = colLo = colHi = -1;
+            nwScore[0] = nwScore[1] = lcScore[0] = lcScore[1] = kScoreNone;
+            lcRow[0] = lcRow[1] = -1;
+            nextBH = kSW ? negGo : NEGV; nextBF = nextBH;
+            if (!firstPass && t == 0 && Tmax > 0) { nextBH = bH[0]; nextBF = bF[0]; }
+        };
 
         // residues of column cc as (y0 + 1) | (y1 + 1) << 8, 0 = none.  The paired stream is padded, so
         // only the upper clamp is needed (a group may idle while longer groups of its warp finish).
@@ -339,183 +347,207 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
             if (LANES == 2) return ps[min(cc, Tmax)];
             return (cc >= 0 && cc < Tmax) ? (uint32_t)seq0[cc] + 1u : 0u;
         };
-        int c = -t;
-        uint32_t wnext = fetch(c);
-        reg P[R];
-        if (kPrefetchP) {
-            const uint32_t plo0 = myLo + (wnext & 0xffu) * rowBytes, phi0 = myHi + (wnext >> 8) * rowBytes;
-#pragma unroll
-            for (int v = 0; v < (R + 3) / 4; v++) load_chunk(P, plo0, phi0, v);
-        }
+        // One sweep of the task with tracking flavor TRACK (kFlavorSWEndFast tasks whose score leaves the exact
+        // range of the key are swept a second time with kFlavorSWEnd, see below).
+        auto sweep = [&](auto trackTag) {
+            constexpr int TRACK = decltype(trackTag)::value;
+            int c = -t;
+            uint32_t wnext = fetch(c);
+            reg P[R];
+            if (kPrefetchP) {
+                const uint32_t plo0 = myLo + (wnext & 0xffu) * rowBytes, phi0 = myHi + (wnext >> 8) * rowBytes;
+    #pragma unroll
+                for (int v = 0; v < (R + 3) / 4; v++) load_chunk(P, plo0, phi0, v);
+            }
 
-        for (int s = 0; s < steps; s++, c++) {
-            // ---- (H - Go, F) handed down by the row above, for column c
-            reg upH = __shfl_up_sync(0xffffffffu, outH, 1, G);
-            reg upF = __shfl_up_sync(0xffffffffu, outF, 1, G);
-            {   // thread 0 has no thread above: row -1 of the matrix (first pass) or the previous pass's
-                // boundary row.  Written as selects / predicated loads: a per-step divergent branch here
-                // costs more than the whole exchange.
-                reg synH, synF;
-                if (firstPass) {
-                    synH = TR::splat((mode == kModeNW ? -Go - c * Ge : 0) - Go);  // row -1, reference :716-732
-                    synF = synH;  // F entering row 0 = max(-inf - Ge, H[-1][c] - Go)
-                } else {
-                    synH = nextBH; synF = nextBF;
-                    nextBH = kSW ? negGo : NEGV; nextBF = nextBH;
-                    if (t == 0 && c + 1 < Tmax) { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
-                }
-                upH = (t == 0) ? synH : upH;
-                upF = (t == 0) ? synF : upF;
-            }
-            const uint32_t wcur = wnext;
-            wnext = fetch(c + 1);
-            const bool active = c >= 0 && c < Tmax;
-            // SW runs its idle columns too: with the "no residue" letter they leave a state that is
-            // equivalent to the initial one (H = 0, negative E/F never matter) and cannot raise best.
-            if (!kSW && !active) continue;
-
-            // ---- one target column for this thread's R query rows.
-            // Per cell (Gotoh, reference src/opal.cpp:280-328 / :748-772), with X = max(diag + P, E [, 0]):
-            //   H = max(X, F);  F' = max(F - Ge, H - Go) = max(F - min(Ge, Go), X - Go).
-            // So the only value carried from row to row is F (one VIADDMNMX per row on the critical
-            // path); E, X and X - Go of every row depend on the previous column only.  Row j+1's X is
-            // issued before row j's H is written back, which lets H - Go be updated in place.
-            // Profile values of this column.  Short strips (R <= 20) keep P[] live across steps and reload each
-            // 4-row chunk for the NEXT column as soon as it has been consumed, which takes the shared-memory
-            // latency off the critical path of a warp that runs alone on its scheduler partition.
-            const uint32_t plo = myLo + (wcur & 0xffu) * rowBytes, phi = myHi + (wcur >> 8) * rowBytes;
-            const uint32_t ploNext = myLo + (wnext & 0xffu) * rowBytes, phiNext = myHi + (wnext >> 8) * rowBytes;
-            if (!kPrefetchP) load_chunk(P, plo, phi, 0);
-            auto consumed = [&](int row) {  // P[row] has just been used
-                if (kPrefetchP) { if (row % 4 == 3 || row == R - 1) load_chunk(P, ploNext, phiNext, row / 4); }
-                else if (row % 4 == 3 && row + 1 < R) load_chunk(P, plo, phi, row / 4 + 1);
-            };
-            reg f = upF;
-            const reg dIn = diag;
-            diag = upH;
-            const reg bestBefore = best;
-            reg e0 = TR::addmax(E[0], negGe, HG[0]);
-            E[0] = e0;
-            reg X = kSW ? TR::addmax_relu(dIn, P[0], e0) : TR::addmax(dIn, P[0], e0);
-            consumed(0);
-            reg Xprev = 0;
-#pragma unroll
-            for (int j = 0; j < R; j++) {
-                reg Xn = 0;
-                if (j + 1 < R) {
-                    const reg e1 = TR::addmax(E[j + 1], negGe, HG[j + 1]);
-                    E[j + 1] = e1;
-                    Xn = kSW ? TR::addmax_relu(HG[j], P[j + 1], e1) : TR::addmax(HG[j], P[j + 1], e1);
-                }
-                if (j + 1 < R) consumed(j + 1);
-                if (FLAVOR == kFlavorSWScore) {
-                    if (j & 1) best = TR::vmax3(best, Xprev, X); else Xprev = X;
-                } else if (FLAVOR == kFlavorSWEnd) {
-                    best = TR::track(best, X, rowLo, rowHi, j, p.one);
-                } else if (FLAVOR == kFlavorSWEndFast) {
-                    // key = H << 6 | (63 - row) in both half-words: one IMAD (FMA pipe) and one VIMNMX.  Exact while
-                    // H < 512; larger scores are detected at the end (fastEndLimit) and re-run by kFlavorSWEnd.
-                    const uint32_t rowBits = (uint32_t)((1 << kRowBits) - 1 - j) * 0x00010001u;
-                    best = TR::vmax(best, (reg)((uint32_t)X * (uint32_t)p.keyScale + rowBits));
-                }
-                const reg XG = TR::add(X, negGo);
-                HG[j] = TR::addmax(f, negGo, XG);   // H - Go = max(X, F) - Go
-                f = TR::addmax(f, negGmin, XG);     // F of the next row
-                X = Xn;
-            }
-            if (FLAVOR == kFlavorSWScore && (R & 1)) best = TR::vmax(best, Xprev);
-            const reg u = HG[R - 1];
-            outH = u; outF = f;
-
-            if (FLAVOR == kFlavorSWEnd) {
-                const reg ch = best ^ bestBefore;
-                if (LANES == 2) { if (ch & 0xffffu) colLo = c; if (ch >> 16) colHi = c; }
-                else if (ch) colLo = c;
-            }
-            if (FLAVOR == kFlavorSWEndFast) {
-                // A changed half-word means a strictly larger (score, first row) in THIS column: latch row and
-                // column, then saturate the row bits so that equal scores of later columns cannot win.
-                const uint32_t b = (uint32_t)best, ch = b ^ (uint32_t)bestBefore;
-                const int mask = (1 << kRowBits) - 1;
-                if (ch & 0xffffu) { colLo = c; rowLo = mask - (int)(b & mask); }
-                if (ch >> 16) { colHi = c; rowHi = mask - (int)((b >> 16) & mask); }
-                best = (reg)(b | (uint32_t)mask * 0x00010001u);
-            }
-            if (FLAVOR == kFlavorGlobal) {
-                if (mode == kModeNW) {
-                    if (lastPass && t == tLast) {
-#pragma unroll
-                        for (int l = 0; l < LANES; l++)
-                            if (c == T[l] - 1) {
-                                reg v = HG[0];
-#pragma unroll
-                                for (int j = 1; j < R; j++) if (j == jLast) v = HG[j];
-                                nwScore[l] = TR::lane(v, l) + Go;
-                            }
+            for (int s = 0; s < steps; s++, c++) {
+                // ---- (H - Go, F) handed down by the row above, for column c
+                reg upH = __shfl_up_sync(0xffffffffu, outH, 1, G);
+                reg upF = __shfl_up_sync(0xffffffffu, outF, 1, G);
+                {   // thread 0 has no thread above: row -1 of the matrix (first pass) or the previous pass's
+                    // boundary row.  Written as selects / predicated loads: a per-step divergent branch here
+                    // costs more than the whole exchange.
+                    reg synH, synF;
+                    if (firstPass) {
+                        if (kSW) synH = negGo;  // row -1 is all zeros
+                        else synH = TR::splat((mode == kModeNW ? -Go - c * Ge : 0) - Go);  // row -1, reference :716-732
+                        synF = synH;  // F entering row 0 = max(-inf - Ge, H[-1][c] - Go)
+                    } else {
+                        synH = nextBH; synF = nextBF;
+                        nextBH = kSW ? negGo : NEGV; nextBF = nextBH;
+                        if (t == 0 && c + 1 < Tmax) { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
                     }
-                } else {
-                    // last query row (HW, OV): register R-1 of thread G-1 in the last pass
-                    if (lastPass && t == G - 1) {
-                        reg cand = u;
-                        if (LANES == 2) cand = TR::pack(c < T[0] ? TR::lane(u, 0) : TR::NEG, c < T[1] ? TR::lane(u, 1) : TR::NEG);
-                        bool ph, pl;
-                        best = TR::bmax(best, cand, &ph, &pl);
-                        if (!pl) colLo = c;
-                        if (LANES == 2 && !ph) colHi = c;
+                    upH = (t == 0) ? synH : upH;
+                    upF = (t == 0) ? synF : upF;
+                }
+                const uint32_t wcur = wnext;
+                wnext = fetch(c + 1);
+                const bool active = c >= 0 && c < Tmax;
+                // SW runs its idle columns too: with the "no residue" letter they leave a state that is
+                // equivalent to the initial one (H = 0, negative E/F never matter) and cannot raise best.
+                if (!kSW && !active) continue;
+
+                // ---- one target column for this thread's R query rows.
+                // Per cell (Gotoh, reference src/opal.cpp:280-328 / :748-772), with X = max(diag + P, E [, 0]):
+                //   H = max(X, F);  F' = max(F - Ge, H - Go) = max(F - min(Ge, Go), X - Go).
+                // So the only value carried from row to row is F (one VIADDMNMX per row on the critical
+                // path); E, X and X - Go of every row depend on the previous column only.  Row j+1's X is
+                // issued before row j's H is written back, which lets H - Go be updated in place.
+                // Profile values of this column.  Short strips (R <= 20) keep P[] live across steps and reload each
+                // 4-row chunk for the NEXT column as soon as it has been consumed, which takes the shared-memory
+                // latency off the critical path of a warp that runs alone on its scheduler partition.
+                const uint32_t plo = myLo + (wcur & 0xffu) * rowBytes, phi = myHi + (wcur >> 8) * rowBytes;
+                const uint32_t ploNext = myLo + (wnext & 0xffu) * rowBytes, phiNext = myHi + (wnext >> 8) * rowBytes;
+                if (!kPrefetchP) load_chunk(P, plo, phi, 0);
+                auto consumed = [&](int row) {  // P[row] has just been used
+                    if (kPrefetchP) { if (row % 4 == 3 || row == R - 1) load_chunk(P, ploNext, phiNext, row / 4); }
+                    else if (row % 4 == 3 && row + 1 < R) load_chunk(P, plo, phi, row / 4 + 1);
+                };
+                reg f = upF;
+                const reg dIn = diag;
+                diag = upH;
+                const reg bestBefore = best;
+                reg e0 = TR::addmax(E[0], negGe, HG[0]);
+                E[0] = e0;
+                reg X = kSW ? TR::addmax_relu(dIn, P[0], e0) : TR::addmax(dIn, P[0], e0);
+                consumed(0);
+    #pragma unroll
+                for (int j = 0; j < R; j++) {
+                    reg Xn = 0;
+                    if (j + 1 < R) {
+                        const reg e1 = TR::addmax(E[j + 1], negGe, HG[j + 1]);
+                        E[j + 1] = e1;
+                        Xn = kSW ? TR::addmax_relu(HG[j], P[j + 1], e1) : TR::addmax(HG[j], P[j + 1], e1);
                     }
-                    // last target column (OV): every real row of this thread
-                    if (mode == kModeOV) {
-#pragma unroll
-                        for (int l = 0; l < LANES; l++)
-                            if (c == T[l] - 1) {
-#pragma unroll
-                                for (int j = 0; j < R; j++) {
-                                    const int r = myRow0 + j;
-                                    const int v = TR::lane(HG[j], l) + Go;
-                                    if (r >= 0 && r < p.Q && v > lcScore[l]) { lcScore[l] = v; lcRow[l] = r; }
+                    if (j + 1 < R) consumed(j + 1);
+                    if (TRACK == kFlavorSWScore) {
+                        best = TR::vmax(best, X);  // ptxas pairs these into VIMNMX3.S16x2 (0.5 instruction per cell)
+                    } else if (TRACK == kFlavorSWEnd) {
+                        best = TR::track(best, X, rowLo, rowHi, j, p.one);
+                    } else if (TRACK == kFlavorSWEndFast) {
+                        // key = H << 6 | (63 - row) in both half-words: one IMAD (FMA pipe) and one VIMNMX.  Exact while
+                        // H < 512; larger scores are detected at the end (fastEndLimit) and re-run by kFlavorSWEnd.
+                        const uint32_t rowBits = (uint32_t)((1 << kRowBits) - 1 - j) * 0x00010001u;
+                        best = TR::vmax(best, (reg)((uint32_t)X * (uint32_t)p.keyScale + rowBits));
+                    }
+                    const reg XG = TR::add(X, negGo);
+                    HG[j] = TR::addmax(f, negGo, XG);   // H - Go = max(X, F) - Go
+                    f = TR::addmax(f, negGmin, XG);     // F of the next row
+                    X = Xn;
+                }
+                const reg u = HG[R - 1];
+                outH = u; outF = f;
+
+                if (TRACK == kFlavorSWEnd) {
+                    const reg ch = best ^ bestBefore;
+                    if (LANES == 2) { if (ch & 0xffffu) colLo = c; if (ch >> 16) colHi = c; }
+                    else if (ch) colLo = c;
+                }
+                if (TRACK == kFlavorSWEndFast) {
+                    // A changed half-word means a strictly larger (score, first row) in THIS column: latch row and
+                    // column, then saturate the row bits so that equal scores of later columns cannot win.
+                    const uint32_t b = (uint32_t)best, ch = b ^ (uint32_t)bestBefore;
+                    const int mask = (1 << kRowBits) - 1;
+                    if (ch & 0xffffu) { colLo = c; rowLo = mask - (int)(b & mask); }
+                    if (ch >> 16) { colHi = c; rowHi = mask - (int)((b >> 16) & mask); }
+                    best = (reg)(b | (uint32_t)mask * 0x00010001u);
+                }
+                if (FLAVOR == kFlavorGlobal) {
+                    if (mode == kModeNW) {
+                        if (lastPass && t == tLast) {
+    #pragma unroll
+                            for (int l = 0; l < LANES; l++)
+                                if (c == T[l] - 1) {
+                                    reg v = HG[0];
+    #pragma unroll
+                                    for (int j = 1; j < R; j++) if (j == jLast) v = HG[j];
+                                    nwScore[l] = TR::lane(v, l) + Go;
                                 }
-                            }
+                        }
+                    } else {
+                        // last query row (HW, OV): register R-1 of thread G-1 in the last pass
+                        if (lastPass && t == G - 1) {
+                            reg cand = u;
+                            if (LANES == 2) cand = TR::pack(c < T[0] ? TR::lane(u, 0) : TR::NEG, c < T[1] ? TR::lane(u, 1) : TR::NEG);
+                            bool ph, pl;
+                            best = TR::bmax(best, cand, &ph, &pl);
+                            if (!pl) colLo = c;
+                            if (LANES == 2 && !ph) colHi = c;
+                        }
+                        // last target column (OV): every real row of this thread
+                        if (mode == kModeOV) {
+    #pragma unroll
+                            for (int l = 0; l < LANES; l++)
+                                if (c == T[l] - 1) {
+    #pragma unroll
+                                    for (int j = 0; j < R; j++) {
+                                        const int r = myRow0 + j;
+                                        const int v = TR::lane(HG[j], l) + Go;
+                                        if (r >= 0 && r < p.Q && v > lcScore[l]) { lcScore[l] = v; lcRow[l] = r; }
+                                    }
+                                }
+                        }
+                    }
+                }
+                if (!lastPass) {  // kernel-uniform: single-pass searches skip the boundary row entirely
+                    if (t == G - 1 && active) {
+                        reinterpret_cast<reg*>(p.bndOutH)[off0 + c] = outH;
+                        reinterpret_cast<reg*>(p.bndOutF)[off0 + c] = outF;
                     }
                 }
             }
-            if (!lastPass && t == G - 1 && active) {
-                reinterpret_cast<reg*>(p.bndH)[off0 + c] = outH;
-                reinterpret_cast<reg*>(p.bndF)[off0 + c] = outF;
-            }
-        }
 
-        // ---- reduce the group's candidates and merge them into the running results
+        };
+
+        // ---- reduce the group's candidates (key: score desc, target index asc, query index asc)
         int fsc[2], fcc[2], frr[2];
+        auto reduce = [&](bool keyTracking) {
 #pragma unroll
-        for (int l = 0; l < LANES; l++) {
-            int sc = kScoreNone, cc = 0x7fffffff, rr = 0x7fffffff;  // this thread's candidate
-            if (kSW) {
-                sc = TR::lane(best, l);
-                if (FLAVOR == kFlavorSWEndFast) sc >>= kRowBits;
-                if ((FLAVOR == kFlavorSWEnd || FLAVOR == kFlavorSWEndFast) && sc > 0) { cc = l ? colHi : colLo; rr = myRow0 + (l ? rowHi : rowLo); }
-            } else if (mode == kModeNW) {
-                sc = nwScore[l]; cc = T[l] - 1; rr = p.Q - 1;
-            } else {
-                if (lastPass && t == G - 1 && T[l] > 0) { sc = TR::lane(best, l) + Go; cc = l ? colHi : colLo; rr = p.Q - 1; }
-                if (mode == kModeOV && lcScore[l] != kScoreNone && better(lcScore[l], T[l] - 1, lcRow[l], sc, cc, rr)) {
-                    sc = lcScore[l]; cc = T[l] - 1; rr = lcRow[l];
+            for (int l = 0; l < LANES; l++) {
+                int sc = kScoreNone, cc = 0x7fffffff, rr = 0x7fffffff;  // this thread's candidate
+                if (kSW) {
+                    sc = TR::lane(best, l);
+                    if (keyTracking) sc >>= kRowBits;
+                    if ((FLAVOR == kFlavorSWEnd || FLAVOR == kFlavorSWEndFast) && sc > 0) { cc = l ? colHi : colLo; rr = myRow0 + (l ? rowHi : rowLo); }
+                } else if (mode == kModeNW) {
+                    sc = nwScore[l]; cc = T[l] - 1; rr = p.Q - 1;
+                } else {
+                    if (lastPass && t == G - 1 && T[l] > 0) { sc = TR::lane(best, l) + Go; cc = l ? colHi : colLo; rr = p.Q - 1; }
+                    if (mode == kModeOV && lcScore[l] != kScoreNone && better(lcScore[l], T[l] - 1, lcRow[l], sc, cc, rr)) {
+                        sc = lcScore[l]; cc = T[l] - 1; rr = lcRow[l];
+                    }
                 }
+                for (int o = 1; o < G; o <<= 1) {
+                    const int s2 = __shfl_xor_sync(0xffffffffu, sc, o);
+                    const int c2 = __shfl_xor_sync(0xffffffffu, cc, o);
+                    const int r2 = __shfl_xor_sync(0xffffffffu, rr, o);
+                    if (better(s2, c2, r2, sc, cc, rr)) { sc = s2; cc = c2; rr = r2; }
+                }
+                fsc[l] = sc; fcc[l] = cc; frr[l] = rr;
             }
-            for (int o = 1; o < G; o <<= 1) {
-                const int s2 = __shfl_xor_sync(0xffffffffu, sc, o);
-                const int c2 = __shfl_xor_sync(0xffffffffu, cc, o);
-                const int r2 = __shfl_xor_sync(0xffffffffu, rr, o);
-                if (better(s2, c2, r2, sc, cc, rr)) { sc = s2; cc = c2; rr = r2; }
-            }
-            fsc[l] = sc; fcc[l] = cc; frr[l] = rr;
-        }
-        // kFlavorSWEndFast: a half-word whose score left the exact range may also have spilled into its
-        // neighbour, so the whole pair is handed to the exact flavor.
-        bool pairInexact = false;
+        };
+
         if (FLAVOR == kFlavorSWEndFast) {
+            // Key tracking is exact while scores stay below fastEndLimit.  A half-word that left that range may
+            // also have spilled into its neighbour, so if any pair of this warp is affected the warp sweeps its
+            // tasks once more with the exact per-cell predicate tracking (same registers, second code path).
+            init_state(true);
+            sweep(std::integral_constant<int, kFlavorSWEndFast>());
+            reduce(true);
+            bool inexact = false;
 #pragma unroll
-            for (int l = 0; l < LANES; l++) pairInexact |= fsc[l] >= p.fastEndLimit;
+            for (int l = 0; l < LANES; l++) inexact |= fsc[l] >= p.fastEndLimit;
+            if (__any_sync(0xffffffffu, inexact)) {
+                init_state(false);
+                sweep(std::integral_constant<int, kFlavorSWEnd>());
+                reduce(false);
+            }
+        } else {
+            init_state(false);
+            sweep(std::integral_constant<int, FLAVOR>());
+            reduce(false);
         }
+        const bool pairInexact = false;
 #pragma unroll
         for (int l = 0; l < LANES; l++) {
             if (t == 0 && tgt[l] >= 0) {
@@ -545,7 +577,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
 // Register-only loop of the SW cell recurrence (6 packed instructions per 2 cells) used by
 // bench.py to measure the integer-pipe roofline on the device it runs on.
 template <int ILP>
-__global__ void __launch_bounds__(kBlockThreads, 1) dpx_peak_kernel(uint32_t* out, int iters, uint32_t seed) {
+__global__ void __launch_bounds__(512, 1) dpx_peak_kernel(uint32_t* out, int iters, uint32_t seed) {
     uint32_t h[ILP], e[ILP], f[ILP], b[ILP];
 #pragma unroll
     for (int i = 0; i < ILP; i++) { h[i] = seed + i * 0x00010001u + threadIdx.x; e[i] = h[i] ^ 0x00050003u; f[i] = e[i] + 0x00010002u; b[i] = 0; }
