@@ -51,9 +51,9 @@ int opalb200_db_search(OpalB200Db* handle, const unsigned char query[], int quer
 
 /* Statistics of the last search on this handle: kernels launched, targets re-run in 32 bits, and the
  * geometry of the last launched class (threads per target pair, query rows per thread, passes over the
- * query, resident warps per SM scheduler partition). Any pointer may be NULL. */
+ * query, resident warps per SM scheduler partition), and the number of concurrent launch groups. Any pointer may be NULL. */
 void opalb200_db_last_stats(const OpalB200Db* handle, int* kernelLaunches, int* rerun32, int* G, int* R, int* passes,
-                            int* warpsPerPartition);
+                            int* warpsPerPartition, int* groups);
 
 /*
  * Measures the packed-DPX issue rate of `device` with a register-only kernel running the SW cell

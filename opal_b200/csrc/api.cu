@@ -154,7 +154,7 @@ int opalb200_db_search(OpalB200Db* h, const unsigned char query[], int queryLeng
 }
 
 void opalb200_db_last_stats(const OpalB200Db* h, int* kernelLaunches, int* rerun32, int* G, int* R, int* passes,
-                            int* warpsPerPartition) {
+                            int* warpsPerPartition, int* groups) {
     const SearchStats& s = reinterpret_cast<const DeviceDb*>(h)->stats();
     if (kernelLaunches) *kernelLaunches = s.kernelLaunches;
     if (rerun32) *rerun32 = s.rerun32;
@@ -162,6 +162,7 @@ void opalb200_db_last_stats(const OpalB200Db* h, int* kernelLaunches, int* rerun
     if (R) *R = s.R;
     if (passes) *passes = s.passes;
     if (warpsPerPartition) *warpsPerPartition = s.warpsPerPartition;
+    if (groups) *groups = s.groups;
 }
 
 double opalb200_measure_dpx_peak(int device, double* threadInstrPerSec, float* ms) {

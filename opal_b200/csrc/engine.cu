@@ -179,81 +179,94 @@ static bool device_info(int device, DeviceInfo* out) {
 // 16-byte units, so the 8 lanes of a quarter-warp hit 8 different bank groups whatever their residues are.
 static int rpad_of(int R) { const int r4 = (R + 3) / 4; return 4 * ((r4 % 2 == 0) ? r4 + 1 : r4); }
 
-// Picks (G, R, passes, warps per scheduler partition) for a query of Q rows.
+// Task lengths of one class (longest first) with strided prefix sums, so that the planner can price any
+// contiguous range of tasks under any group size in O(1).
+struct TaskLens {
+    std::vector<int> len;
+    std::vector<double> prefix[6];  // prefix[s][k] = sum of len[i] over i = 0, g, 2g, ... < k*g with g = 1 << s
+    void build() {
+        for (int sh = 0; sh < 6; sh++) {
+            const size_t g = (size_t)1 << sh, cnt = (len.size() + g - 1) / g;
+            prefix[sh].assign(cnt + 1, 0.0);
+            for (size_t k = 0; k < cnt; k++) prefix[sh][k + 1] = prefix[sh][k] + len[k * g];
+        }
+    }
+    // sum of len[i] for i = lo, lo+g, ... < hi  (lo must be a multiple of g = 1 << sh), and how many terms
+    double strided(int sh, size_t lo, size_t hi, double* terms) const {
+        const size_t g = (size_t)1 << sh, a = lo / g, b = (hi + g - 1) / g;
+        *terms = (double)(b - a);
+        return prefix[sh][b] - prefix[sh][a];
+    }
+};
+
+// Picks (G, R, passes, warps per scheduler partition) for a query of Q rows over `taskLens` (one entry
+// per task, longest first) on `numSMs` SMs, and returns the estimated cycles in *estCycles.
 //
-// Timing model (cycles), calibrated on B200 runs (profiles/): the integer pipe retires one packed DPX
-// instruction per 2 cycles per partition and a cell pair costs ~5.5 of them (11 cycles per row ideal,
-// 14.5 measured with the profile loads and adds around them); a step of one warp alone costs another
-// ~160 cycles of exposed latency (exchange, residue fetch, profile load).  With k warps sharing a
-// partition that latency is hidden, so one step of one warp lasts max(k * 14.5 R, 14.5 R + 160).  Two bounds:
+// Timing model (cycles), fitted to B200 runs (profiles/): the integer pipe retires one packed DPX
+// instruction per 2 cycles per partition and a cell pair costs ~5.5 of them (11 cycles per row ideal).
+// Measured: one warp alone on its partition takes 17.75 R + 104 cycles per step (exposed latencies);
+// two warps sharing a partition take 2 (12.8 R + 57) per step each.  Two bounds:
 //   throughput:  sum over warp-tasks of steps * stepTime / (partitions * k)
 //   tail:        the longest target's steps * stepTime  (it cannot be split across warps)
 // Small databases with a long tail (BASELINE configs[1]) are tail-bound and want G = 32 and k = 1;
-// large ones are throughput-bound and want few threads per target and k = 4.
-static bool pick_geometry(int Q, int A, int lanes, const std::vector<int>& lens, int smemLimit, int numSMs, int mode,
-                          Geometry* out) {
+// large ones are throughput-bound and want fewer threads per target and k = 2.
+static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo, size_t hi, int smemLimit, int numSMs, int mode,
+                          bool latencyClass, Geometry* out, double* estCycles) {
     const int planes = lanes == 2 ? 2 : 1;
     const auto& tables = kernel_tables();
     double bestCost = 1e300;
     bool found = false;
-    // sum of lengths and the longest length; lens is sorted longest first and tasks pair neighbours
-    double sumLen = 0;
-    for (size_t i = 0; i < lens.size(); i += lanes) sumLen += lens[i];
-    const double tasks = (double)((lens.size() + lanes - 1) / lanes);
-    const double maxLen = lens.empty() ? 0 : lens[0];
-    for (size_t ti = 0; ti < tables.size(); ti++) {
+    const double tasks = (double)(hi - lo);
+    const double maxLen = hi > lo ? tl.len[lo] : 0;
+    auto consider = [&](size_t ti, int G, int k, bool forced) {
         const int R = tables[ti].R;
         const int Rpad = rpad_of(R);
-        for (int G = 1; G <= 32; G *= 2) {
-            const int rowStride = (G * Rpad + 31) / 32 * 32;
-            const size_t smem = (size_t)planes * (A + 1) * rowStride * 4;
-            if (smem > (size_t)smemLimit) continue;
-            const int rows = G * R;
-            const int passes = (Q + rows - 1) / rows;
-            const double groupsPerWarp = 32.0 / G;
-            const double warpSteps = (sumLen + tasks * (G - 1)) / groupsPerWarp;  // per pass
-            const double warpTasks = std::max(1.0, tasks / groupsPerWarp);
-            for (int k = 1; k <= kBlockThreads / 128; k *= 2) {
-                // with fewer warp-tasks than resident warps the partitions are not shared k ways
-                const double kEff = std::max(1.0, std::min((double)k, std::ceil(warpTasks / (numSMs * 4.0))));
-                const double stepTime = std::max(kEff * 14.5 * R, 14.5 * R + 160.0);
-                const double warpsBusy = std::min((double)numSMs * 4 * k, warpTasks);
-                const double throughput = warpSteps * stepTime / warpsBusy;
-                const double tail = (maxLen + G - 1) * stepTime;
-                const double cost = passes * (std::max(throughput, tail) + 0.15 * std::min(throughput, tail) + 4000.0);
-                if (cost < bestCost) {
-                    bestCost = cost;
-                    found = true;
-                    out->G = G; out->R = R; out->tableIndex = (int)ti; out->passes = passes; out->Rpad = Rpad;
-                    out->rowStride = rowStride; out->smemBytes = smem; out->warpsPerPartition = k;
-                    out->padTop = (mode == kModeNW) ? 0 : passes * rows - Q;
-                }
-            }
+        const int rowStride = (G * Rpad + 31) / 32 * 32;
+        const size_t smem = (size_t)planes * (A + 1) * rowStride * 4;
+        if (smem > (size_t)smemLimit) return;
+        const int rows = G * R;
+        const int passes = (Q + rows - 1) / rows;
+        const int groupsPerWarp = 32 / G;
+        // a warp-task lasts as long as its longest group: every groupsPerWarp-th task of the sorted list
+        int sh = 0;
+        while ((1 << sh) < groupsPerWarp) sh++;
+        double warpTasks = 1;
+        double warpSteps = tl.strided(sh, lo, hi, &warpTasks);
+        warpSteps += warpTasks * (G - 1);
+        warpTasks = std::max(1.0, warpTasks);
+        // with fewer warp-tasks than resident warps the partitions are not shared k ways
+        const double kEff = std::max(1.0, std::min((double)k, std::ceil(warpTasks / (numSMs * 4.0))));
+        const double stepTime = kEff < 1.5 ? 17.75 * R + 104.0 : kEff * (12.8 * R + 57.0);
+        const double warpsBusy = std::min((double)numSMs * 4 * k, warpTasks);
+        const double throughput = warpSteps * stepTime / warpsBusy;
+        const double tail = (maxLen + G - 1) * stepTime;
+        // every further pass is a kernel of its own (drain, launch, boundary rows through HBM): measured ~4 % each
+        const double cost = passes * (std::max(throughput, tail) + 0.15 * std::min(throughput, tail) + 30000.0) *
+                            (1.0 + 0.04 * (passes - 1));
+        if (forced || cost < bestCost) {
+            bestCost = cost;
+            found = true;
+            out->G = G; out->R = R; out->tableIndex = (int)ti; out->passes = passes; out->Rpad = Rpad;
+            out->rowStride = rowStride; out->smemBytes = smem; out->warpsPerPartition = k;
+            out->padTop = (mode == kModeNW) ? 0 : passes * rows - Q;
         }
-    }
+    };
+    for (size_t ti = 0; ti < tables.size(); ti++)
+        for (int G = latencyClass ? 32 : 1; G <= 32; G *= 2)
+            for (int k = 1; k <= (latencyClass ? 1 : kBlockThreads / 128); k *= 2) consider(ti, G, k, false);
     // Development override: OPAL_B200_GEOMETRY="G,R,k" forces a geometry (ignored when it does not fit).
     if (const char* env = getenv("OPAL_B200_GEOMETRY")) {
         int G = 0, R = 0, k = 0;
-        if (sscanf(env, "%d,%d,%d", &G, &R, &k) == 3 && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && k >= 1 && k <= kBlockThreads / 128) {
-            for (size_t ti = 0; ti < tables.size(); ti++) {
-                if (tables[ti].R != R) continue;
-                const int Rpad = rpad_of(R), rowStride = (G * Rpad + 31) / 32 * 32;
-                const size_t smem = (size_t)planes * (A + 1) * rowStride * 4;
-                if (smem > (size_t)smemLimit) break;
-                const int rows = G * R, passes = (Q + rows - 1) / rows;
-                out->G = G; out->R = R; out->tableIndex = (int)ti; out->passes = passes; out->Rpad = Rpad;
-                out->rowStride = rowStride; out->smemBytes = smem; out->warpsPerPartition = k;
-                out->padTop = (mode == kModeNW) ? 0 : passes * rows - Q;
-                found = true;
-            }
-        }
+        if (!latencyClass && sscanf(env, "%d,%d,%d", &G, &R, &k) == 3 && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && k >= 1 &&
+            k <= kBlockThreads / 128)
+            for (size_t ti = 0; ti < tables.size(); ti++)
+                if (tables[ti].R == R) consider(ti, G, k, true);
     }
     if (!found) set_error("alphabet too large for the shared-memory query profile");
+    if (estCycles) *estCycles = bestCost;
     return found;
 }
 
-// ---------------------------------------------------------------- database packing
-// Builds the paired stream from the plain length-sorted residues: one warp per target pair.
 static __global__ void pack_pairs_kernel(const uint8_t* residues, const long long* offsets, const int* lengths, int numTargets,
                                   const long long* pairOffsets, int numPairs, uint16_t* pairStream, int* maxCode) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -294,7 +307,8 @@ DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int
         if (di.major < 10) { set_error("device is not sm_100 or newer"); return false; }
         d->numSMs_ = di.numSMs;
         d->smemLimit_ = di.smemLimit;
-        if (!stream_acquire(device, &d->stream_) || !event_acquire(device, &d->evStart_) || !event_acquire(device, &d->evStop_)) return false;
+        if (!stream_acquire(device, &d->stream_) || !event_acquire(device, &d->evStart_) || !event_acquire(device, &d->evStop_) ||
+            !event_acquire(device, &d->evFork_)) return false;
 
         // ---- sort by length, longest first (counting sort; stable in caller order)
         int maxLen = 0;
@@ -360,7 +374,7 @@ DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int
         if (!device_alloc(device, (void**)&d->dScore_, nInts)) return false;
         if (!device_alloc(device, (void**)&d->dEndQ_, nInts)) return false;
         if (!device_alloc(device, (void**)&d->dEndT_, nInts)) return false;
-        if (!device_alloc(device, (void**)&d->dTaskList_, nInts)) return false;
+        if (!device_alloc(device, (void**)&d->dTaskList_, 2 * nInts)) return false;
         if (!device_alloc(device, (void**)&d->dCounters_, sizeof(int) * 256)) return false;
         if (!pinned_alloc((void**)&d->hScore_, nInts)) return false;
         if (!pinned_alloc((void**)&d->hEndQ_, nInts)) return false;
@@ -396,7 +410,9 @@ DeviceDb::~DeviceDb() {
     void* dev[] = {dResidues_, dOffsets_, dLengths_, dScore_, dEndQ_, dEndT_, dTaskList_, dCounters_, dBndH_, dBndF_, dQuery_, dMatrix_, dPairStream_, dPairOffsets_, dMaxCode_};
     for (void* p : dev) device_release(device_, p);
     pinned_release(hScore_); pinned_release(hEndQ_); pinned_release(hEndT_);
-    event_release(device_, evStart_); event_release(device_, evStop_);
+    event_release(device_, evStart_); event_release(device_, evStop_); event_release(device_, evFork_);
+    for (cudaStream_t st : auxStreams_) { cudaStreamSynchronize(st); stream_release(device_, st); }
+    for (cudaEvent_t e : auxEvents_) event_release(device_, e);
     stream_release(device_, stream_);
 }
 
@@ -407,18 +423,22 @@ bool DeviceDb::ensure_boundary() {
     return true;
 }
 
-// Runs every pass of one precision class over `list` (sorted positions, longest first).
-int DeviceDb::run_class(int type, const std::vector<int>& list, const unsigned char* dQuery, const int* dMatrix, int Q,
-                        int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot) {
-    if (list.empty()) return 0;
-    const int lanes = type == 0 ? 2 : 1;
-    std::vector<int> lens(list.size());
-    for (size_t k = 0; k < list.size(); k++) lens[k] = sortedLen_[list[k]];
+// One kernel-launch group: tasks that share a precision class and a geometry.
+struct DeviceDb::Group {
+    int type = 0;            // 0 = Packed16 (tasks are pair indices), 1 = Scalar32 (tasks are sorted-target indices)
+    std::vector<int> tasks;  // longest first
     Geometry g;
-    if (!pick_geometry(Q, A, lanes, lens, smemLimit_, numSMs_, mode, &g)) return OPAL_B200_ERR_CUDA;
-    if (g.passes > 1 && !ensure_boundary()) return OPAL_B200_ERR_CUDA;
-    if (*launchSlot + g.passes > 256) { set_error("too many passes"); return OPAL_B200_ERR_CUDA; }
+    size_t smemBytes = 0;    // dynamic shared memory requested (>= g.smemBytes, see exclusive placement below)
+    int maxBlocks = 0;
+};
 
+// Splits one precision class into launch groups.  A database whose longest targets would keep single warps
+// busy long after everything else has finished (the tail bound of pick_geometry) gets a "latency class":
+// its longest tasks run with 32 threads per task and one warp per scheduler partition on SMs of their own,
+// concurrently with the throughput-oriented bulk group on the remaining SMs.
+bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, int mode, std::vector<Group>* groups) {
+    if (list.empty()) return true;
+    const int lanes = type == 0 ? 2 : 1;
     // Packed16 works on the pairs fixed at packing time (targets 2p, 2p+1): a pair runs if either member
     // is wanted; results of unwanted members are simply not published.
     std::vector<int> tasks;
@@ -427,49 +447,142 @@ int DeviceDb::run_class(int type, const std::vector<int>& list, const unsigned c
     } else {
         tasks = list;
     }
-    const bool identity = (int)tasks.size() == (lanes == 2 ? numPairs_ : n_);
-    auto okc = [&]() -> bool {
-        if (!identity)
-            CUDA_TRY(cudaMemcpyAsync(dTaskList_, tasks.data(), sizeof(int) * tasks.size(), cudaMemcpyHostToDevice, stream_));
-        // SW score+end at 16 bits uses the key-tracking flavor: exact below fastEndLimit, and warps that meet a
-        // larger score sweep their tasks again with the exact per-cell tracking inside the same kernel.
-        const int fastEndLimit = (32768 >> kRowBits) - std::max(maxScore, 0) - 1;
-        const bool fastEnd = mode == kModeSW && wantEnd && type == 0 && g.R <= (1 << kRowBits) && fastEndLimit >= 64 &&
-                             !getenv("OPAL_B200_EXACT_END");
-        const int flavor = (mode == kModeSW) ? (wantEnd ? (fastEnd ? kFlavorSWEndFast : kFlavorSWEnd) : kFlavorSWScore) : kFlavorGlobal;
-        const void* fn = kernel_tables()[g.tableIndex].fn[type * 4 + flavor];
-        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smemBytes));
-        for (int pass = 0; pass < g.passes; pass++) {
-            SearchParams p;
-            memset(&p, 0, sizeof(p));
-            p.query = dQuery; p.matrix = dMatrix; p.Q = Q; p.A = A; p.gapOpen = Go; p.gapExt = Ge; p.mode = mode;
-            p.wantEnd = wantEnd;
-            p.G = g.G; p.rowBase = pass * g.G * g.R; p.padTop = g.padTop; p.pass = pass; p.numPasses = g.passes;
-            p.rowStride = g.rowStride; p.Rpad = g.Rpad;
-            p.residues = dResidues_; p.offsets = dOffsets_; p.lengths = dLengths_;
-            p.pairStream = dPairStream_; p.pairOffsets = dPairOffsets_; p.numTargets = n_;
-            p.taskList = identity ? nullptr : dTaskList_;
-            p.numTasks = (int)tasks.size();
-            p.counter = dCounters_ + (*launchSlot)++;
-            const size_t half = (size_t)(totalResidues_ + 64);
-            p.bndInH = dBndH_ ? dBndH_ + ((pass + 1) & 1) * half : nullptr; p.bndInF = dBndF_ ? dBndF_ + ((pass + 1) & 1) * half : nullptr;
-            p.bndOutH = dBndH_ ? dBndH_ + (pass & 1) * half : nullptr; p.bndOutF = dBndF_ ? dBndF_ + (pass & 1) * half : nullptr;
-            p.outScore = dScore_; p.outEndQ = dEndQ_; p.outEndT = dEndT_;
-            p.overflowLimit = type == 0 ? 32767 - std::max(maxScore, 0) - 1 : (1 << 30);
-            p.padLetterScore = type == 0 ? -16384 : 0;
-            p.one = 1; p.keyScale = 1 << kRowBits; p.fastEndLimit = fastEndLimit;
-            void* args[] = {&p};
-            const int warpsPerBlock = 4 * g.warpsPerPartition;  // one block per SM, k warps per scheduler partition
-            const long long warpsNeeded = ((long long)tasks.size() * g.G + 31) / 32;
-            const int blocks = (int)std::max<long long>(1, std::min<long long>(numSMs_, (warpsNeeded + warpsPerBlock - 1) / warpsPerBlock));
-            CUDA_TRY(cudaLaunchKernel(fn, dim3(blocks), dim3(32 * warpsPerBlock), args, g.smemBytes, stream_));
-            stats_.kernelLaunches++;
+    TaskLens tl;
+    tl.len.resize(tasks.size());
+    for (size_t k = 0; k < tasks.size(); k++) tl.len[k] = sortedLen_[lanes == 2 ? 2 * tasks[k] : tasks[k]];
+    tl.build();
+    const size_t nT = tasks.size();
+
+    Geometry gAll;
+    double tAll = 0;
+    if (!pick_geometry(Q, A, lanes, tl, 0, nT, smemLimit_, numSMs_, mode, false, &gAll, &tAll)) return false;
+    // candidate splits: the m longest tasks form the latency class on smL SMs
+    double bestT = tAll;
+    size_t bestM = 0;
+    int bestSm = 0;
+    Geometry bestL, bestB;
+    if (!getenv("OPAL_B200_NO_SPLIT") && !getenv("OPAL_B200_GEOMETRY")) {
+        for (size_t m = 32; m * 2 <= nT && m <= 4096; m *= 2) {  // multiples of 32 keep every group size aligned
+            for (int div = 1; div <= 4; div *= 2) {
+                const int smL = (int)std::min<size_t>((m + 4 * div - 1) / (4 * div), (size_t)numSMs_ / 2);
+                if (smL < 1) continue;
+                Geometry gL, gB;
+                double tL = 0, tB = 0;
+                if (!pick_geometry(Q, A, lanes, tl, 0, m, smemLimit_, smL, mode, true, &gL, &tL)) continue;
+                if (!pick_geometry(Q, A, lanes, tl, m, nT, smemLimit_, numSMs_ - smL, mode, false, &gB, &tB)) continue;
+                const double t = std::max(tL, tB) + 3000.0;  // a second launch is not free
+                if (t < bestT * 0.97) { bestT = t; bestM = m; bestSm = smL; bestL = gL; bestB = gB; }
+            }
+        }
+    }
+    auto add = [&](size_t lo, size_t hi, const Geometry& g, int maxBlocks, size_t otherSmem) {
+        Group grp;
+        grp.type = type;
+        grp.tasks.assign(tasks.begin() + lo, tasks.begin() + hi);
+        grp.g = g;
+        grp.maxBlocks = maxBlocks;
+        grp.smemBytes = g.smemBytes;
+        // exclusive placement: ask for enough shared memory that a block of the other group cannot join this SM
+        if (otherSmem > 0 && g.smemBytes + otherSmem <= (size_t)smemLimit_)
+            grp.smemBytes = std::min<size_t>((size_t)smemLimit_, (size_t)smemLimit_ - otherSmem + 1024);
+        groups->push_back(std::move(grp));
+    };
+    if (bestM == 0) add(0, tasks.size(), gAll, numSMs_, 0);
+    else {
+        add(0, bestM, bestL, bestSm, bestB.smemBytes);   // launched first: takes its SMs
+        // every block's first tasks are assigned statically (longest first), so the bulk grid must be fully
+        // resident from the start: one block per SM the latency class leaves free
+        add(bestM, tasks.size(), bestB, numSMs_ - bestSm, 0);
+    }
+    return true;
+}
+
+// Launches every pass of one group on `stream`.
+bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t stream, const unsigned char* dQuery,
+                            const int* dMatrix, int Q, int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot) {
+    const Geometry& g = grp.g;
+    const int type = grp.type;
+    if (g.passes > 1 && !ensure_boundary()) return false;
+    if (*launchSlot + g.passes > 256) { set_error("too many passes"); return false; }
+    // contiguous task ranges need no list in device memory
+    bool contiguous = true;
+    for (size_t k = 1; k < grp.tasks.size() && contiguous; k++) contiguous = grp.tasks[k] == grp.tasks[k - 1] + 1;
+    if (!contiguous)
+        CUDA_TRY(cudaMemcpyAsync(taskListDevice, grp.tasks.data(), sizeof(int) * grp.tasks.size(), cudaMemcpyHostToDevice, stream));
+    // SW score+end at 16 bits uses the key-tracking flavor: exact below fastEndLimit, and warps that meet a
+    // larger score sweep their tasks again with the exact per-cell tracking inside the same kernel.
+    const int fastEndLimit = (32768 >> kRowBits) - std::max(maxScore, 0) - 1;
+    const bool fastEnd = mode == kModeSW && wantEnd && type == 0 && g.R <= (1 << kRowBits) && fastEndLimit >= 64 &&
+                         !getenv("OPAL_B200_EXACT_END");
+    const int flavor = (mode == kModeSW) ? (wantEnd ? (fastEnd ? kFlavorSWEndFast : kFlavorSWEnd) : kFlavorSWScore) : kFlavorGlobal;
+    const void* fn = kernel_tables()[g.tableIndex].fn[type * 4 + flavor];
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grp.smemBytes));
+    for (int pass = 0; pass < g.passes; pass++) {
+        SearchParams p;
+        memset(&p, 0, sizeof(p));
+        p.query = dQuery; p.matrix = dMatrix; p.Q = Q; p.A = A; p.gapOpen = Go; p.gapExt = Ge; p.mode = mode;
+        p.wantEnd = wantEnd;
+        p.G = g.G; p.rowBase = pass * g.G * g.R; p.padTop = g.padTop; p.pass = pass; p.numPasses = g.passes;
+        p.rowStride = g.rowStride; p.Rpad = g.Rpad;
+        p.residues = dResidues_; p.offsets = dOffsets_; p.lengths = dLengths_;
+        p.pairStream = dPairStream_; p.pairOffsets = dPairOffsets_; p.numTargets = n_;
+        p.taskList = contiguous ? nullptr : taskListDevice;
+        p.taskBase = contiguous && !grp.tasks.empty() ? grp.tasks[0] : 0;
+        p.numTasks = (int)grp.tasks.size();
+        p.counter = dCounters_ + (*launchSlot)++;
+        const size_t half = (size_t)(totalResidues_ + 64);
+        p.bndInH = dBndH_ ? dBndH_ + ((pass + 1) & 1) * half : nullptr; p.bndInF = dBndF_ ? dBndF_ + ((pass + 1) & 1) * half : nullptr;
+        p.bndOutH = dBndH_ ? dBndH_ + (pass & 1) * half : nullptr; p.bndOutF = dBndF_ ? dBndF_ + (pass & 1) * half : nullptr;
+        p.outScore = dScore_; p.outEndQ = dEndQ_; p.outEndT = dEndT_;
+        p.overflowLimit = type == 0 ? 32767 - std::max(maxScore, 0) - 1 : (1 << 30);
+        p.padLetterScore = type == 0 ? -16384 : 0;
+        p.one = 1; p.keyScale = 1 << kRowBits; p.fastEndLimit = fastEndLimit;
+        void* args[] = {&p};
+        const int warpsPerBlock = 4 * g.warpsPerPartition;  // one block per SM, k warps per scheduler partition
+        const long long warpsNeeded = ((long long)grp.tasks.size() * g.G + 31) / 32;
+        const int blocks = (int)std::max<long long>(1, std::min<long long>(grp.maxBlocks, (warpsNeeded + warpsPerBlock - 1) / warpsPerBlock));
+        CUDA_TRY(cudaLaunchKernel(fn, dim3(blocks), dim3(32 * warpsPerBlock), args, grp.smemBytes, stream));
+        stats_.kernelLaunches++;
+    }
+    stats_.G = g.G; stats_.R = g.R; stats_.passes = g.passes; stats_.warpsPerPartition = g.warpsPerPartition;
+    return true;
+}
+
+// Runs the given classes concurrently: every launch group gets a stream of its own (the first one the
+// database's main stream), all of them ordered after `ready` and joined back into the main stream.
+int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int>*>>& classes, const unsigned char* dQuery,
+                          const int* dMatrix, int Q, int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot) {
+    std::vector<Group> groups;
+    for (auto& c : classes)
+        if (!plan_class(c.first, *c.second, Q, A, mode, &groups)) return OPAL_B200_ERR_CUDA;
+    if (groups.empty()) return 0;
+    stats_.groups = (int)groups.size();
+    auto body = [&]() -> bool {
+        size_t listOffset = 0;
+        if (!startRecorded_) { CUDA_TRY(cudaEventRecord(evStart_, stream_)); startRecorded_ = true; }  // planning is host work: keep it outside the device window
+        if (groups.size() > 1) CUDA_TRY(cudaEventRecord(evFork_, stream_));
+        for (size_t gi = 0; gi < groups.size(); gi++) {
+            cudaStream_t st = stream_;
+            if (gi > 0) {
+                while (auxStreams_.size() < gi) {
+                    cudaStream_t s2; cudaEvent_t e2;
+                    if (!stream_acquire(device_, &s2) || !event_acquire(device_, &e2)) return false;
+                    auxStreams_.push_back(s2); auxEvents_.push_back(e2);
+                }
+                st = auxStreams_[gi - 1];
+                CUDA_TRY(cudaStreamWaitEvent(st, evFork_, 0));
+            }
+            if (!launch_group(groups[gi], dTaskList_ + listOffset, st, dQuery, dMatrix, Q, Go, Ge, A, wantEnd, mode, maxScore, launchSlot))
+                return false;
+            listOffset += groups[gi].tasks.size();
+            if (gi > 0) {
+                CUDA_TRY(cudaEventRecord(auxEvents_[gi - 1], st));
+                CUDA_TRY(cudaStreamWaitEvent(stream_, auxEvents_[gi - 1], 0));
+            }
         }
         return true;
-    }();
-    if (!okc) return OPAL_B200_ERR_CUDA;
-    stats_.G = g.G; stats_.R = g.R; stats_.passes = g.passes; stats_.warpsPerPartition = g.warpsPerPartition;
-    return 0;
+    };
+    return body() ? 0 : OPAL_B200_ERR_CUDA;
 }
 
 int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const int* matrix, int A, int wantEnd, int mode,
@@ -532,6 +645,20 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
         }
     }
     if (!touched) return 0;
+    // The 16-bit class works on whole pairs (sorted targets 2p, 2p+1) and the two classes of NW/HW/OV run
+    // concurrently, so a pair is never split between them: if one member needs 32 bits, both go there.
+    if (!isSW && !list32.empty() && !list16.empty()) {
+        std::vector<char> wide((size_t)numPairs_, 0);
+        for (int p : list32) wide[p >> 1] = 1;
+        std::vector<int> keep16, merged32;
+        for (int p : list16) (wide[p >> 1] ? merged32 : keep16).push_back(p);
+        if (!merged32.empty()) {
+            std::vector<int> all(list32.size() + merged32.size());
+            std::merge(list32.begin(), list32.end(), merged32.begin(), merged32.end(), all.begin());
+            list32.swap(all);
+            list16.swap(keep16);
+        }
+    }
 
     unsigned char* dQuery = nullptr;
     int* dMatrix = nullptr;
@@ -549,7 +676,7 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
         CUDA_TRY(cudaMemcpyAsync(dMatrix, matrix, sizeof(int) * A * A, cudaMemcpyHostToDevice, stream_));
         CUDA_TRY(cudaMemsetAsync(dCounters_, 0, sizeof(int) * 256, stream_));
         int slot = 0;
-        CUDA_TRY(cudaEventRecord(evStart_, stream_));
+        startRecorded_ = false;
         auto fetch = [&]() -> bool {
             const size_t nInts = sizeof(int) * (size_t)n_;
             CUDA_TRY(cudaMemcpyAsync(hScore_, dScore_, nInts, cudaMemcpyDeviceToHost, stream_));
@@ -570,13 +697,19 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
                 if (endT) endT[i] = (wantEnd && hEndT_[p] != 0x7fffffff) ? hEndT_[p] : -1;
             }
         };
-        if (!list16.empty()) {
-            rc = run_class(0, list16, dQuery, dMatrix, Q, Go, Ge, A, wantEnd, mode, maxP, &slot);
+        // NW/HW/OV classes are independent (routed a priori) and run concurrently; SW's 32-bit class is the
+        // re-run of what overflowed 16 bits and has to follow it.
+        std::vector<std::pair<int, const std::vector<int>*>> first;
+        if (!list16.empty()) first.push_back({0, &list16});
+        if (!isSW && !list32.empty()) first.push_back({1, &list32});
+        if (!first.empty()) {
+            rc = run_classes(first, dQuery, dMatrix, Q, Go, Ge, A, wantEnd, mode, maxP, &slot);
             if (rc) return rc != OPAL_B200_ERR_CUDA;
             CUDA_TRY(cudaEventRecord(evStop_, stream_));
             if (!fetch()) return false;
             std::vector<int> again;
-            publish(list16, &again);
+            publish(list16, isSW ? &again : nullptr);
+            if (!isSW) publish(list32, nullptr);
             if (!again.empty()) {
                 stats_.rerun32 = (int)again.size();
                 std::vector<int> merged(list32.size() + again.size());
@@ -584,14 +717,15 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
                 list32.swap(merged);
             }
         }
-        if (!list32.empty()) {
-            rc = run_class(1, list32, dQuery, dMatrix, Q, Go, Ge, A, wantEnd, mode, maxP, &slot);
+        if (isSW && !list32.empty()) {
+            std::vector<std::pair<int, const std::vector<int>*>> second = {{1, &list32}};
+            rc = run_classes(second, dQuery, dMatrix, Q, Go, Ge, A, wantEnd, mode, maxP, &slot);
             if (rc) return rc != OPAL_B200_ERR_CUDA;
             CUDA_TRY(cudaEventRecord(evStop_, stream_));
             if (!fetch()) return false;
             publish(list32, nullptr);
         }
-        if (deviceMs) CUDA_TRY(cudaEventElapsedTime(deviceMs, evStart_, evStop_));
+        if (deviceMs && startRecorded_) CUDA_TRY(cudaEventElapsedTime(deviceMs, evStart_, evStop_));
         return true;
     };
     const bool okb = body();

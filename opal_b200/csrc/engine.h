@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace opalb200 {
@@ -25,7 +26,7 @@ struct Geometry {
 };
 
 struct SearchStats {
-    int kernelLaunches = 0, rerun32 = 0, G = 0, R = 0, passes = 0, warpsPerPartition = 0;
+    int kernelLaunches = 0, rerun32 = 0, G = 0, R = 0, passes = 0, warpsPerPartition = 0, groups = 0;
 };
 
 void set_error(const std::string& msg);
@@ -56,8 +57,12 @@ public:
 
 private:
     DeviceDb() {}
-    int run_class(int type, const std::vector<int>& list, const unsigned char* dQuery, const int* dMatrix, int Q, int Go,
-                  int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot);
+    struct Group;
+    bool plan_class(int type, const std::vector<int>& list, int Q, int A, int mode, std::vector<Group>* groups);
+    bool launch_group(const Group& grp, int* taskListDevice, cudaStream_t stream, const unsigned char* dQuery, const int* dMatrix,
+                      int Q, int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot);
+    int run_classes(const std::vector<std::pair<int, const std::vector<int>*>>& classes, const unsigned char* dQuery,
+                    const int* dMatrix, int Q, int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot);
     bool ensure_boundary();
 
     int device_ = 0, n_ = 0, numSMs_ = 0, smemLimit_ = 0;
@@ -78,8 +83,11 @@ private:
     size_t queryCapacity_ = 0;
     int *hScore_ = nullptr, *hEndQ_ = nullptr, *hEndT_ = nullptr;  // pinned
     cudaStream_t stream_ = nullptr;
-    cudaEvent_t evStart_ = nullptr, evStop_ = nullptr;
+    cudaEvent_t evStart_ = nullptr, evStop_ = nullptr, evFork_ = nullptr;
+    std::vector<cudaStream_t> auxStreams_;
+    std::vector<cudaEvent_t> auxEvents_;
     SearchStats stats_;
+    bool startRecorded_ = false;
 };
 
 double measure_dpx_peak(int device, double* threadInstrPerSec, float* ms);

@@ -65,6 +65,7 @@ struct SearchParams {
     int numTargets;       // targets in the database (the last pair may have one member)
     // work: Packed16 tasks are pair indices, Scalar32 tasks are target indices (taskList null = 0..numTasks-1)
     const int* taskList;
+    int taskBase;         // first task when taskList is null
     int numTasks;
     int* counter;
     // boundary row between passes, indexed by residue offset of the task's first target + column; a pass
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchPa
         const uint8_t* seq0 = p.residues;
         long long off0 = 0;
         if (taskIdx < p.numTasks) {
-            const int task = p.taskList ? p.taskList[taskIdx] : taskIdx;
+            const int task = p.taskList ? p.taskList[taskIdx] : p.taskBase + taskIdx;
             if (LANES == 2) {
                 tgt[0] = 2 * task;
                 tgt[1] = (2 * task + 1 < p.numTargets) ? 2 * task + 1 : -1;

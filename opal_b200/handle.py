@@ -36,7 +36,7 @@ class OpalB200(OpalCLibrary):
         L.opalb200_db_residues.restype = ctypes.c_longlong
         L.opalb200_db_search.argtypes = [vp, vp, ci, ci, ci, vp, ci, ci, ci, vp, vp, vp, vp, vp]
         L.opalb200_db_search.restype = ci
-        L.opalb200_db_last_stats.argtypes = [vp] + [ctypes.POINTER(ci)] * 6
+        L.opalb200_db_last_stats.argtypes = [vp] + [ctypes.POINTER(ci)] * 7
         L.opalb200_db_last_stats.restype = None
         L.opalb200_measure_dpx_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]
         L.opalb200_measure_dpx_peak.restype = ctypes.c_double
@@ -85,9 +85,9 @@ class ResidentDb:
         return rc, sc, eq, et, float(ms.value)
 
     def last_stats(self):
-        v = [ctypes.c_int(0) for _ in range(6)]
+        v = [ctypes.c_int(0) for _ in range(7)]
         self.eng.lib.opalb200_db_last_stats(self.handle, *[ctypes.byref(x) for x in v])
-        return dict(zip(("kernel_launches", "rerun32", "G", "R", "passes", "warps_per_partition"), (x.value for x in v)))
+        return dict(zip(("kernel_launches", "rerun32", "G", "R", "passes", "warps_per_partition", "groups"), (x.value for x in v)))
 
     def close(self):
         if self.handle:
