@@ -3,6 +3,8 @@
 // opalSearchDatabase mirrors reference src/opal.cpp:1435-1519 step by step -- skip mask from
 // prefilled records, score/end search, early return on error, then either the alignment stage
 // or the "no alignment" field fill -- with the SIMD passes replaced by DeviceDb::search.
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -53,11 +55,18 @@ int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db
         anyWork |= !skip[i];
     }
     const int wantEnd = searchType != OPAL_SEARCH_SCORE;
+    const bool trace = getenv("OPAL_B200_TRACE") != nullptr;  // phase timings of the drop-in call on stderr
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto t0 = now();
     DeviceDb* ddb = nullptr;
     if (anyWork || searchType == OPAL_SEARCH_ALIGNMENT) {
         ddb = DeviceDb::create(db, dbLength, dbSeqLengths, default_device());
         if (!ddb) return OPAL_ERR_NO_SIMD_SUPPORT;
     }
+    const auto t1 = now();
     int status = 0;
     if (anyWork) {
         std::vector<int> sc(dbLength), eq(dbLength, -1), et(dbLength, -1);
@@ -72,10 +81,15 @@ int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db
             }
         }
     }
+    const auto t2 = now();
     if (status == 0 && searchType == OPAL_SEARCH_ALIGNMENT)
         status = align_database(ddb, query, queryLength, db, dbLength, dbSeqLengths, gapOpen, gapExt, scoreMatrix, alphabetLength,
                                 results, mode);
+    const auto t3 = now();
     delete ddb;
+    if (trace)
+        fprintf(stderr, "[opal-b200] pack+upload %.3f ms, search %.3f ms, alignment %.3f ms, release %.3f ms\n", ms(t0, t1), ms(t1, t2),
+                ms(t2, t3), ms(t3, now()));
     if (status) return status;  // :1473
     if (searchType != OPAL_SEARCH_ALIGNMENT) {  // :1508-1515
         for (int i = 0; i < dbLength; i++) {

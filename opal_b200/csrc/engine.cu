@@ -345,7 +345,8 @@ DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int
         uint8_t* staging = nullptr;
         if (!pinned_alloc((void**)&staging, bytes)) return false;
         memset(staging + total, 0, 64);
-        int nThreads = (int)std::min<long long>(std::max(1u, std::thread::hardware_concurrency()), 1 + total / (1 << 20));
+        // host threads only pay off for large databases (spawning them costs more than copying a few MB)
+        int nThreads = total < (32 << 20) ? 1 : (int)std::min<long long>(std::max(1u, std::thread::hardware_concurrency()), total / (8 << 20));
         nThreads = std::max(1, std::min(nThreads, 32));
         auto gather = [&](int lo, int hi) {
             for (int p = lo; p < hi; p++)
