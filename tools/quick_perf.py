@@ -29,7 +29,7 @@ def main():
     if which != "config2":
         want = [int(x) for x in os.environ.get("QLENS", "144,375,1000,2005,5478").split(",")]
         queries += [(f"Q{len(x)}", x) for x in datasets.config3_queries(sm) if len(x) in want]
-    modes = ("SW", "NW", "HW", "OV") if which == "config2" else ("SW", "NW")
+    modes = tuple(os.environ["MODES"].split(",")) if "MODES" in os.environ else (("SW", "NW", "HW", "OV") if which == "config2" else ("SW", "NW"))
     for name, qq in queries:
         for mode in modes:
             for st in (0, 1):
