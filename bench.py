@@ -176,10 +176,12 @@ def run_b200_arm(args, rank, local_rank, world):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; opal-b200 has no CPU path")
     torch.cuda.set_device(local_rank)
+    os.environ["OPAL_B200_DEVICE"] = str(local_rank)  # device of the drop-in entry points (they take no device argument)
+    dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -188,13 +190,13 @@ def run_b200_arm(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     def sum_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
@@ -204,7 +206,7 @@ def run_b200_arm(args, rank, local_rank, world):
     mat, A, Q = sm.flat(), sm.alphabet_length, int(len(query))
     handle = eng.create_db(db, local_rank)
     cells_rank = Q * db.total_residues
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step_resident():
         flush.zero_()

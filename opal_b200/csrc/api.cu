@@ -16,6 +16,13 @@
 
 using namespace opalb200;
 
+// The CUDA "current device" is per-thread state of the caller: entry points put it back on return.
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) saved = -1; }
+    ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
 static int default_device() {
     const char* e = getenv("OPAL_B200_DEVICE");
     return e ? atoi(e) : 0;
@@ -41,6 +48,7 @@ void opalSearchResultSetScore(OpalSearchResult* r, int score) {  // :1561-1564
 int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db[], int dbLength, int dbSeqLengths[],
                        int gapOpen, int gapExt, int* scoreMatrix, int alphabetLength, OpalSearchResult* results[],
                        const int searchType, int mode, int overflowMethod) {
+    DeviceGuard guard;
     (void)overflowMethod;  // OPAL_OVERFLOW_SIMPLE / _BUCKETS only schedule the reference's passes; results are equal
     if (mode != OPAL_MODE_NW && mode != OPAL_MODE_HW && mode != OPAL_MODE_OV && mode != OPAL_MODE_SW)
         return OPAL_ERR_INVALID_MODE;  // :1469-1473, results untouched
@@ -111,6 +119,7 @@ int opalSearchDatabaseRescore(unsigned char query[], int queryLength, unsigned c
 
 int opalSearchDatabaseCharSW(unsigned char query[], int queryLength, unsigned char** db, int dbLength, int dbSeqLengths[],
                              int gapOpen, int gapExt, int* scoreMatrix, int alphabetLength, OpalSearchResult* results[]) {
+    DeviceGuard guard;
     // reference src/opal.cpp:1522-1546: SW scores that fit 8 bits; the others come back unset (-1).
     if (dbLength <= 0) return 0;
     bool argsFit = !(gapOpen < -128 || 127 < gapOpen || gapExt < -128 || 127 < gapExt);  // :178-180
@@ -149,10 +158,14 @@ int opalb200_device_count(void) {
 const char* opalb200_last_error(void) { return last_error(); }
 
 OpalB200Db* opalb200_db_create(unsigned char* db[], int dbLength, const int dbSeqLengths[], int device) {
+    DeviceGuard guard;
     return reinterpret_cast<OpalB200Db*>(DeviceDb::create(db, dbLength, dbSeqLengths, device));
 }
 
-void opalb200_db_destroy(OpalB200Db* h) { delete reinterpret_cast<DeviceDb*>(h); }
+void opalb200_db_destroy(OpalB200Db* h) {
+    DeviceGuard guard;
+    delete reinterpret_cast<DeviceDb*>(h);
+}
 
 int opalb200_db_length(const OpalB200Db* h) { return reinterpret_cast<const DeviceDb*>(h)->size(); }
 
@@ -162,6 +175,7 @@ int opalb200_db_search(OpalB200Db* h, const unsigned char query[], int queryLeng
                        const int* scoreMatrix, int alphabetLength, int searchType, int mode, const unsigned char* skip,
                        int* scores, int* endQuery, int* endTarget, float* deviceMs) {
     if (!h || !scores) return OPAL_ERR_NO_SIMD_SUPPORT;
+    DeviceGuard guard;
     const int wantEnd = searchType != OPAL_SEARCH_SCORE && endQuery && endTarget;
     return reinterpret_cast<DeviceDb*>(h)->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd,
                                                   mode, skip, scores, endQuery, endTarget, deviceMs);
@@ -180,6 +194,7 @@ void opalb200_db_last_stats(const OpalB200Db* h, int* kernelLaunches, int* rerun
 }
 
 double opalb200_measure_dpx_peak(int device, double* threadInstrPerSec, float* ms) {
+    DeviceGuard guard;
     return measure_dpx_peak(device, threadInstrPerSec, ms);
 }
 
