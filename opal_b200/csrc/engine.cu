@@ -431,6 +431,7 @@ struct DeviceDb::Group {
     Geometry g;
     size_t smemBytes = 0;    // dynamic shared memory requested (>= g.smemBytes, see exclusive placement below)
     int maxBlocks = 0;
+    double estCycles = 0;    // planner's estimate, used to share SMs between concurrent groups
 };
 
 // Splits one precision class into launch groups.  A database whose longest targets would keep single warps
@@ -476,9 +477,10 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
             }
         }
     }
-    auto add = [&](size_t lo, size_t hi, const Geometry& g, int maxBlocks, size_t otherSmem) {
+    auto add = [&](size_t lo, size_t hi, const Geometry& g, int maxBlocks, size_t otherSmem, double est) {
         Group grp;
         grp.type = type;
+        grp.estCycles = est;
         grp.tasks.assign(tasks.begin() + lo, tasks.begin() + hi);
         grp.g = g;
         grp.maxBlocks = maxBlocks;
@@ -488,12 +490,12 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
             grp.smemBytes = std::min<size_t>((size_t)smemLimit_, (size_t)smemLimit_ - otherSmem + 1024);
         groups->push_back(std::move(grp));
     };
-    if (bestM == 0) add(0, tasks.size(), gAll, numSMs_, 0);
+    if (bestM == 0) add(0, tasks.size(), gAll, numSMs_, 0, tAll);
     else {
-        add(0, bestM, bestL, bestSm, bestB.smemBytes);   // launched first: takes its SMs
+        add(0, bestM, bestL, bestSm, bestB.smemBytes, bestT);   // launched first: takes its SMs
         // every block's first tasks are assigned statically (longest first), so the bulk grid must be fully
         // resident from the start: one block per SM the latency class leaves free
-        add(bestM, tasks.size(), bestB, numSMs_ - bestSm, 0);
+        add(bestM, tasks.size(), bestB, numSMs_ - bestSm, 0, bestT);
     }
     return true;
 }
@@ -558,6 +560,33 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
         if (!plan_class(c.first, *c.second, Q, A, mode, &groups)) return OPAL_B200_ERR_CUDA;
     if (groups.empty()) return 0;
     stats_.groups = (int)groups.size();
+    // Concurrent groups own disjoint SMs (grids are persistent, one block per SM, and every block must be
+    // resident from the start because first tasks are assigned statically).  Small groups -- the latency
+    // class, a handful of 32-bit targets -- get the blocks they can fill and are launched first; the
+    // remaining SMs are shared by the large groups in proportion to their estimated work.
+    if (groups.size() > 1) {
+        auto wanted = [&](const Group& g) {
+            const int wpb = 4 * g.g.warpsPerPartition;
+            const long long warps = ((long long)g.tasks.size() * g.g.G + 31) / 32;
+            return (int)std::max<long long>(1, std::min<long long>(g.maxBlocks, (warps + wpb - 1) / wpb));
+        };
+        std::stable_sort(groups.begin(), groups.end(), [&](const Group& a, const Group& b) { return wanted(a) < wanted(b); });
+        std::vector<int> want(groups.size());
+        std::vector<char> big(groups.size(), 0);
+        for (size_t i = 0; i < groups.size(); i++) want[i] = wanted(groups[i]);
+        int reserved = 0;
+        double bigWork = 0;
+        for (size_t i = 0; i < groups.size(); i++) {
+            if (want[i] * 4 <= numSMs_ && reserved + want[i] <= numSMs_ / 2) { groups[i].maxBlocks = want[i]; reserved += want[i]; }
+            else { big[i] = 1; bigWork += std::max(1.0, groups[i].estCycles * want[i]); }
+        }
+        const int left = numSMs_ - reserved;
+        for (size_t i = 0; i < groups.size(); i++) {
+            if (!big[i]) continue;
+            const int share = std::max(1, (int)(left * std::max(1.0, groups[i].estCycles * want[i]) / bigWork));
+            groups[i].maxBlocks = std::min(share, want[i]);
+        }
+    }
     auto body = [&]() -> bool {
         size_t listOffset = 0;
         if (!startRecorded_) { CUDA_TRY(cudaEventRecord(evStart_, stream_)); startRecorded_ = true; }  // planning is host work: keep it outside the device window
