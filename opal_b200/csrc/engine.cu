@@ -587,6 +587,11 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
             groups[i].maxBlocks = std::min(share, want[i]);
         }
     }
+    if (getenv("OPAL_B200_TRACE"))
+        for (const Group& g : groups)
+            fprintf(stderr, "[opal-b200] group type=%d tasks=%zu longest=%d G=%d R=%d k=%d passes=%d blocks<=%d est=%.0f kcycles\n", g.type,
+                    g.tasks.size(), g.tasks.empty() ? 0 : sortedLen_[g.type == 0 ? 2 * g.tasks[0] : g.tasks[0]], g.g.G, g.g.R,
+                    g.g.warpsPerPartition, g.g.passes, g.maxBlocks, g.estCycles / 1e3);
     auto body = [&]() -> bool {
         size_t listOffset = 0;
         if (!startRecorded_) { CUDA_TRY(cudaEventRecord(evStart_, stream_)); startRecorded_ = true; }  // planning is host work: keep it outside the device window

@@ -12,7 +12,7 @@ import numpy as np
 
 from .capi import MODES, OpalCLibrary, SequenceDB
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libopal_b200.so")
+LIB_PATH = os.environ.get("OPAL_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libopal_b200.so")
 
 
 class OpalB200(OpalCLibrary):
