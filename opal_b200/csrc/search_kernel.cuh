@@ -38,7 +38,10 @@
 
 namespace opalb200 {
 
-constexpr int kBlockThreads = 256;  // at most 2 warps per scheduler partition: measured as fast as 4, and leaves 255 registers per thread
+constexpr int kBlockThreads = 256;  // at most 2 warps per scheduler partition: measured as fast as 3 or 4
+// Register budget hint per flavor (measured on B200): the SW flavors schedule best when ptxas is capped at 170
+// registers (launch bound 384), the NW/HW/OV flavor with the full 255 (launch bound 256).
+constexpr int launch_bound_for(int flavor) { return flavor == 2 ? 256 : 384; }
 constexpr int kModeNW = 0, kModeHW = 1, kModeOV = 2, kModeSW = 3;
 constexpr int kFlavorSWScore = 0, kFlavorSWEnd = 1, kFlavorGlobal = 2, kFlavorSWEndFast = 3;
 constexpr int kRowBits = 6;  // kFlavorSWEndFast: low bits of the tracked key hold 63 - row
@@ -209,7 +212,7 @@ __device__ __forceinline__ bool better(int s, int c, int r, int S, int C, int R)
 // holds the biased score of padded query row rowBase + t*R + j against that letter in its low
 // half-word (sign bits cleared); plane HI holds it shifted left by 16.
 template <int R, int FLAVOR, class TR>
-__global__ void __launch_bounds__(kBlockThreads, 1) search_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(const SearchParams p) {
     typedef typename TR::reg reg;
     constexpr int LANES = TR::LANES;
     constexpr bool kSW = FLAVOR != kFlavorGlobal;
