@@ -17,6 +17,7 @@ extern "C" {
 #endif
 
 typedef struct OpalB200Db OpalB200Db;
+struct OpalSearchResult; /* opal.h */
 
 /* Number of CUDA devices this process can use (0 => every search returns OPAL_ERR_NO_SIMD_SUPPORT). */
 int opalb200_device_count(void);
@@ -30,6 +31,15 @@ const char* opalb200_last_error(void);
  * (reference src/opal.h:107-109).  Returns NULL on failure.
  */
 OpalB200Db* opalb200_db_create(unsigned char* db[], int dbLength, const int dbSeqLengths[], int device);
+/*
+ * Same, from a database that is already packed (the in-memory form of the on-disk format written by
+ * opal_makedb_b200, opal_b200/cli/packed_db.h; replaces the per-run parse + sort of readFastaSequences,
+ * reference src/opal_aligner.cpp:247-301): `residues` holds all sequences back to back, longest first;
+ * sortedLengths[p] is the length of the p-th of them and order[p] the index it has for the caller
+ * (order may be NULL: identity).  Results still come back in caller order.  Returns NULL on failure.
+ */
+OpalB200Db* opalb200_db_create_sorted(const unsigned char* residues, const int sortedLengths[], const int order[],
+                                      int dbLength, int device);
 void opalb200_db_destroy(OpalB200Db* handle);
 
 /* Sequences / residues held by the handle. */
@@ -48,6 +58,28 @@ int opalb200_db_search(OpalB200Db* handle, const unsigned char query[], int quer
                        int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength,
                        int searchType, int mode, const unsigned char* skip,
                        int* scores, int* endQuery, int* endTarget, float* deviceMs);
+
+/*
+ * numQueries searches against the resident database (config 3's protocol: many queries, one database), with up
+ * to `inFlight` (1..8) queries on the device at a time so that the tail of one query overlaps the bulk of the
+ * next and host-side planning / result publishing overlaps kernels.  Same arguments as opalb200_db_search;
+ * outputs are numQueries x dbLength ints, row q = query q, in caller order.  batchMs (nullable) receives the
+ * CUDA-event time from the start of the batch to the last kernel end.
+ */
+int opalb200_db_search_batch(OpalB200Db* handle, int numQueries, const unsigned char* const queries[],
+                             const int queryLengths[], int gapOpen, int gapExt, const int* scoreMatrix,
+                             int alphabetLength, int searchType, int mode,
+                             int* scores, int* endQuery, int* endTarget, int inFlight, float* batchMs);
+
+/*
+ * opalSearchDatabase (reference src/opal.h:150-154) against the resident database: same result records, same
+ * reuse rule for prefilled entries (:118-122), all three search levels including OPAL_SEARCH_ALIGNMENT --
+ * only the db / dbLength / dbSeqLengths arguments are replaced by the handle.  results[] has
+ * opalb200_db_length(handle) entries in caller order.
+ */
+int opalb200_db_search_results(OpalB200Db* handle, const unsigned char query[], int queryLength,
+                               int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength,
+                               struct OpalSearchResult* results[], int searchType, int mode);
 
 /* Statistics of the last search on this handle: kernels launched, targets re-run in 32 bits, and the
  * geometry of the last launched class (threads per target pair, query rows per thread, passes over the

@@ -285,11 +285,21 @@ bool replay_ok(const unsigned char* q, int Q, const unsigned char* t, int T, con
         if (_e != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); ok = false; goto done; } \
     } while (0)
 
+#define ALIGN_OK(expr)                      \
+    do {                                    \
+        if (!(expr)) { ok = false; goto done; } \
+    } while (0)
+
 }  // namespace
 
 int align_database(DeviceDb* ddb, const unsigned char* query, int Q, unsigned char* const* db, int n, const int* lens,
                    int Go, int Ge, const int* matrix, int A, OpalSearchResult* results[], int mode) {
-    if (!ddb) return OPAL_B200_ERR_CUDA;
+    if (!ddb || !ddb->ensure_uploaded()) return OPAL_B200_ERR_CUDA;
+    // target i on the host: the caller's pointer, or (resident-handle calls) the database's own sorted copy
+    auto target_len = [&](int i) { return lens ? lens[i] : ddb->sorted_lengths()[ddb->sorted_position()[i]]; };
+    auto target_ptr = [&](int i) -> const unsigned char* {
+        return db ? db[i] : ddb->h_residues() + ddb->offsets()[ddb->sorted_position()[i]];
+    };
     int M = matrix[0];
     for (int i = 1; i < A * A; i++) M = std::max(M, matrix[i]);
 
@@ -298,7 +308,7 @@ int align_database(DeviceDb* ddb, const unsigned char* query, int Q, unsigned ch
     for (int i = 0; i < n; i++) {
         OpalSearchResult* r = results[i];
         if ((mode == OPAL_MODE_SW && r->score == 0) || r->endLocationQuery < 0 || r->endLocationTarget < 0 ||
-            r->endLocationQuery >= Q || r->endLocationTarget >= lens[i]) {
+            r->endLocationQuery >= Q || r->endLocationTarget >= target_len(i)) {
             r->alignment = NULL;
             r->alignmentLength = 0;
             r->startLocationQuery = r->startLocationTarget = -1;
@@ -326,8 +336,15 @@ int align_database(DeviceDb* ddb, const unsigned char* query, int Q, unsigned ch
     cudaMemGetInfo(&freeB, &totalB);
     const long long budgetWords = (long long)std::max<size_t>(64u << 20, std::min<size_t>(freeB / 3, (size_t)16 << 30)) / 4;
 
-    ALIGN_TRY(cudaMalloc(&dQuery, (size_t)Q + 16));
-    ALIGN_TRY(cudaMalloc(&dMatrix, sizeof(int) * A * A));
+    const int dev = ddb->device();
+    auto dalloc = [&](void* pp, size_t bytes) { return device_alloc(dev, (void**)pp, bytes); };
+    auto release_batch = [&]() {
+        device_release(dev, dTasks); device_release(dev, dOuts); device_release(dev, dFlags); device_release(dev, dEq);
+        device_release(dev, dOps); device_release(dev, dBnd);
+        dTasks = nullptr; dOuts = nullptr; dFlags = nullptr; dEq = nullptr; dOps = nullptr; dBnd = nullptr;
+    };
+    ALIGN_OK(dalloc(&dQuery, (size_t)Q + 16));
+    ALIGN_OK(dalloc(&dMatrix, sizeof(int) * A * A));
     ALIGN_TRY(cudaMemcpyAsync(dQuery, query, Q, cudaMemcpyHostToDevice, stream));
     ALIGN_TRY(cudaMemcpyAsync(dMatrix, matrix, sizeof(int) * A * A, cudaMemcpyHostToDevice, stream));
 
@@ -360,14 +377,13 @@ int align_database(DeviceDb* ddb, const unsigned char* query, int Q, unsigned ch
                     cursor++;
                 }
                 const int nt = (int)tasks.size();
-                cudaFree(dTasks); cudaFree(dOuts); cudaFree(dFlags); cudaFree(dEq); cudaFree(dOps); cudaFree(dBnd);
-                dTasks = nullptr; dOuts = nullptr; dFlags = nullptr; dEq = nullptr; dOps = nullptr; dBnd = nullptr;
-                ALIGN_TRY(cudaMalloc(&dTasks, sizeof(AlignTask) * nt));
-                ALIGN_TRY(cudaMalloc(&dOuts, sizeof(AlignOut) * nt));
-                ALIGN_TRY(cudaMalloc(&dFlags, sizeof(uint32_t) * (size_t)flagWords));
-                ALIGN_TRY(cudaMalloc(&dEq, (size_t)flagWords));
-                ALIGN_TRY(cudaMalloc(&dOps, (size_t)opsBytes));
-                ALIGN_TRY(cudaMalloc(&dBnd, sizeof(int) * (size_t)std::max<long long>(bndInts, 1)));
+                release_batch();  // the previous batch was synchronised before its results were read
+                ALIGN_OK(dalloc(&dTasks, sizeof(AlignTask) * nt));
+                ALIGN_OK(dalloc(&dOuts, sizeof(AlignOut) * nt));
+                ALIGN_OK(dalloc(&dFlags, sizeof(uint32_t) * (size_t)flagWords));
+                ALIGN_OK(dalloc(&dEq, (size_t)flagWords));
+                ALIGN_OK(dalloc(&dOps, (size_t)opsBytes));
+                ALIGN_OK(dalloc(&dBnd, sizeof(int) * (size_t)std::max<long long>(bndInts, 1)));
                 ALIGN_TRY(cudaMemcpyAsync(dTasks, tasks.data(), sizeof(AlignTask) * nt, cudaMemcpyHostToDevice, stream));
                 align_dp_kernel<<<nt, 32, matrixInSmem ? A * A * 4 : 0, stream>>>(dTasks, dOuts, ddb->d_residues(), dQuery, dMatrix, A, Go,
                                                                                    Ge, mode, dFlags, dEq, dBnd, matrixInSmem);
@@ -387,7 +403,7 @@ int align_database(DeviceDb* ddb, const unsigned char* query, int Q, unsigned ch
                     const AlignTask& tk = tasks[k];
                     const unsigned char* ops = hOps.data() + tk.opsOffset;
                     const int sq = tk.endQ - o.endRow, st = tk.endT - o.stopCol;  // src/opal.cpp:1499-1500
-                    const bool good = o.status == 0 && replay_ok(query, Q, db[i], lens[i], ops, o.opsLen, sq, st, tk.endQ, tk.endT,
+                    const bool good = o.status == 0 && replay_ok(query, Q, target_ptr(i), target_len(i), ops, o.opsLen, sq, st, tk.endQ, tk.endT,
                                                                  tk.score, Go, Ge, matrix, A);
                     if (!good && round == 0 && (tk.bottom != tk.Qp - 1 || tk.top != tk.Tp - 1)) { failed.push_back(i); continue; }
                     if (o.status != 0) {  // prefilled score / end inconsistent with the sequences: no alignment exists
@@ -406,7 +422,9 @@ int align_database(DeviceDb* ddb, const unsigned char* query, int Q, unsigned ch
         }
     }
 done:
-    cudaFree(dQuery); cudaFree(dMatrix); cudaFree(dTasks); cudaFree(dOuts); cudaFree(dFlags); cudaFree(dEq); cudaFree(dOps); cudaFree(dBnd);
+    cudaStreamSynchronize(stream);  // nothing may still be using the blocks when they go back to the cache
+    device_release(dev, dQuery); device_release(dev, dMatrix);
+    release_batch();
     return ok ? 0 : OPAL_B200_ERR_CUDA;
 }
 

@@ -45,11 +45,11 @@ void opalSearchResultSetScore(OpalSearchResult* r, int score) {  // :1561-1564
     r->score = score;
 }
 
-int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db[], int dbLength, int dbSeqLengths[],
-                       int gapOpen, int gapExt, int* scoreMatrix, int alphabetLength, OpalSearchResult* results[],
-                       const int searchType, int mode, int overflowMethod) {
-    DeviceGuard guard;
-    (void)overflowMethod;  // OPAL_OVERFLOW_SIMPLE / _BUCKETS only schedule the reference's passes; results are equal
+// The body of opalSearchDatabase once the database is (or can be made) resident.  `ddb` may be NULL: it is
+// then created from db / dbSeqLengths if any entry needs work.  db / dbSeqLengths may be NULL for handle calls.
+static int search_into_results(DeviceDb* ddb, const unsigned char* query, int queryLength, unsigned char* const* db, int dbLength,
+                               const int* dbSeqLengths, int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength,
+                               OpalSearchResult* results[], const int searchType, int mode) {
     if (mode != OPAL_MODE_NW && mode != OPAL_MODE_HW && mode != OPAL_MODE_OV && mode != OPAL_MODE_SW)
         return OPAL_ERR_INVALID_MODE;  // :1469-1473, results untouched
     if (dbLength <= 0) return 0;
@@ -63,15 +63,15 @@ int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db
         anyWork |= !skip[i];
     }
     const int wantEnd = searchType != OPAL_SEARCH_SCORE;
-    const bool trace = getenv("OPAL_B200_TRACE") != nullptr;  // phase timings of the drop-in call on stderr
+    const bool trace = getenv("OPAL_B200_TRACE") != nullptr;  // phase timings of the call on stderr
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double, std::milli>(b - a).count();
     };
     const auto t0 = now();
-    DeviceDb* ddb = nullptr;
-    if (anyWork || searchType == OPAL_SEARCH_ALIGNMENT) {
-        ddb = DeviceDb::create(db, dbLength, dbSeqLengths, default_device());
+    DeviceDb* owned = nullptr;
+    if (!ddb && (anyWork || searchType == OPAL_SEARCH_ALIGNMENT)) {
+        ddb = owned = DeviceDb::create(db, dbLength, dbSeqLengths, default_device());
         if (!ddb) return OPAL_ERR_NO_SIMD_SUPPORT;
     }
     const auto t1 = now();
@@ -94,7 +94,7 @@ int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db
         status = align_database(ddb, query, queryLength, db, dbLength, dbSeqLengths, gapOpen, gapExt, scoreMatrix, alphabetLength,
                                 results, mode);
     const auto t3 = now();
-    delete ddb;
+    delete owned;
     if (trace)
         fprintf(stderr, "[opal-b200] pack+upload %.3f ms, search %.3f ms, alignment %.3f ms, release %.3f ms\n", ms(t0, t1), ms(t1, t2),
                 ms(t2, t3), ms(t3, now()));
@@ -108,6 +108,15 @@ int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db
         }
     }
     return 0;
+}
+
+int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db[], int dbLength, int dbSeqLengths[],
+                       int gapOpen, int gapExt, int* scoreMatrix, int alphabetLength, OpalSearchResult* results[],
+                       const int searchType, int mode, int overflowMethod) {
+    DeviceGuard guard;
+    (void)overflowMethod;  // OPAL_OVERFLOW_SIMPLE / _BUCKETS only schedule the reference's passes; results are equal
+    return search_into_results(nullptr, query, queryLength, db, dbLength, dbSeqLengths, gapOpen, gapExt, scoreMatrix,
+                               alphabetLength, results, searchType, mode);
 }
 
 int opalSearchDatabaseRescore(unsigned char query[], int queryLength, unsigned char* db[], int dbLength, int dbSeqLengths[],
@@ -162,6 +171,13 @@ OpalB200Db* opalb200_db_create(unsigned char* db[], int dbLength, const int dbSe
     return reinterpret_cast<OpalB200Db*>(DeviceDb::create(db, dbLength, dbSeqLengths, device));
 }
 
+OpalB200Db* opalb200_db_create_sorted(const unsigned char* residues, const int sortedLengths[], const int order[], int dbLength,
+                                      int device) {
+    DeviceGuard guard;
+    if (dbLength < 0 || (dbLength > 0 && (!residues || !sortedLengths))) { set_error("invalid packed database"); return nullptr; }
+    return reinterpret_cast<OpalB200Db*>(DeviceDb::create_sorted(residues, sortedLengths, order, dbLength, device));
+}
+
 void opalb200_db_destroy(OpalB200Db* h) {
     DeviceGuard guard;
     delete reinterpret_cast<DeviceDb*>(h);
@@ -179,6 +195,26 @@ int opalb200_db_search(OpalB200Db* h, const unsigned char query[], int queryLeng
     const int wantEnd = searchType != OPAL_SEARCH_SCORE && endQuery && endTarget;
     return reinterpret_cast<DeviceDb*>(h)->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd,
                                                   mode, skip, scores, endQuery, endTarget, deviceMs);
+}
+
+int opalb200_db_search_batch(OpalB200Db* h, int numQueries, const unsigned char* const queries[], const int queryLengths[],
+                             int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength, int searchType, int mode,
+                             int* scores, int* endQuery, int* endTarget, int inFlight, float* batchMs) {
+    if (!h || !scores || (numQueries > 0 && (!queries || !queryLengths))) return OPAL_ERR_NO_SIMD_SUPPORT;
+    DeviceGuard guard;
+    const int wantEnd = searchType != OPAL_SEARCH_SCORE && endQuery && endTarget;
+    return reinterpret_cast<DeviceDb*>(h)->search_batch(numQueries, queries, queryLengths, gapOpen, gapExt, scoreMatrix,
+                                                        alphabetLength, wantEnd, mode, scores, endQuery, endTarget,
+                                                        inFlight <= 0 ? 3 : inFlight, batchMs);
+}
+
+int opalb200_db_search_results(OpalB200Db* h, const unsigned char query[], int queryLength, int gapOpen, int gapExt,
+                               const int* scoreMatrix, int alphabetLength, OpalSearchResult* results[], int searchType, int mode) {
+    if (!h || !results) return OPAL_ERR_NO_SIMD_SUPPORT;
+    DeviceGuard guard;
+    DeviceDb* ddb = reinterpret_cast<DeviceDb*>(h);
+    return search_into_results(ddb, query, queryLength, nullptr, ddb->size(), nullptr, gapOpen, gapExt, scoreMatrix, alphabetLength,
+                               results, searchType, mode);
 }
 
 void opalb200_db_last_stats(const OpalB200Db* h, int* kernelLaunches, int* rerun32, int* G, int* R, int* passes,

@@ -8,6 +8,10 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <climits>
 #include <cstdio>
 #include <cstring>
@@ -33,6 +37,26 @@ const char* last_error() { return g_lastError.c_str(); }
             return false;                                                                    \
         }                                                                                    \
     } while (0)
+
+// ------------------------------------------------------------------ phase tracing (OPAL_B200_TRACE=1)
+namespace {
+struct PhaseTrace {
+    bool on;
+    const char* what;
+    std::chrono::steady_clock::time_point last;
+    std::string line;
+    explicit PhaseTrace(const char* w) : on(getenv("OPAL_B200_TRACE") != nullptr), what(w) { if (on) last = std::chrono::steady_clock::now(); }
+    void mark(const char* phase) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof(buf), " %s %.0f us,", phase, std::chrono::duration<double, std::micro>(now - last).count());
+        line += buf;
+        last = now;
+    }
+    ~PhaseTrace() { if (on && !line.empty()) fprintf(stderr, "[opal-b200] %s:%s\n", what, line.c_str()); }
+};
+}  // namespace
 
 // ------------------------------------------------------------------ kernel registry
 #define OPAL_DECLARE_TABLE(R) const void* const* kernel_table_R##R();
@@ -80,7 +104,7 @@ bool take_block(std::vector<CachedBlock>& list, size_t bytes, void** out, size_t
 }
 }  // namespace
 
-static bool device_alloc(int device, void** p, size_t bytes) {
+bool device_alloc(int device, void** p, size_t bytes) {
     bytes = std::max<size_t>(bytes, 256);
     ResourceCache& c = cache();
     {
@@ -93,7 +117,7 @@ static bool device_alloc(int device, void** p, size_t bytes) {
     c.liveBytes[*p] = bytes;
     return true;
 }
-static void device_release(int device, void* p) {
+void device_release(int device, void* p) {
     if (!p) return;
     ResourceCache& c = cache();
     std::lock_guard<std::mutex> lk(c.mu);
@@ -174,6 +198,93 @@ static bool device_info(int device, DeviceInfo* out) {
     *out = di;
     return true;
 }
+
+// ------------------------------------------------------------------ host worker pool
+// Packing a database is a host-side gather of every sequence into pinned memory; on the drop-in path it is paid
+// per call and is memory-bound on one core, so it is spread over a few persistent threads (the reference arm of
+// the benchmark uses every host thread as well).  The caller takes part in the work; pool threads never touch CUDA.
+namespace {
+class HostPool {
+public:
+    static HostPool& get() { static HostPool* p = new HostPool(); return *p; }  // leaked on purpose, like the cache
+    int width() const { return (int)workers_.size() + 1; }
+    // Runs fn(part) for part in [0, parts); done(part) is called on the calling thread, in part order, as soon as
+    // parts 0..part have all finished.  One job at a time: a second concurrent caller simply runs its job alone.
+    void run(int parts, const std::function<void(int)>& fn, const std::function<void(int)>& done) {
+        std::unique_lock<std::mutex> job(jobMu_, std::try_to_lock);
+        if (!job.owns_lock() || workers_.empty() || parts <= 1) {
+            for (int k = 0; k < parts; k++) { fn(k); done(k); }
+            return;
+        }
+        std::vector<std::atomic<char>> finished((size_t)parts);
+        for (auto& f : finished) f.store(0, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; finished_ = finished.data(); parts_ = parts; next_.store(0); active_ = 0; generation_++;
+        }
+        cv_.notify_all();
+        int reported = 0;
+        auto report = [&]() {
+            while (reported < parts && finished[reported].load(std::memory_order_acquire)) done(reported++);
+        };
+        for (;;) {
+            const int k = next_.fetch_add(1);
+            if (k >= parts) break;
+            fn(k);
+            finished[k].store(1, std::memory_order_release);
+            report();
+        }
+        while (reported < parts) { report(); std::this_thread::yield(); }
+        // workers may still be between "claimed nothing" and going back to sleep: wait until none holds fn_
+        std::unique_lock<std::mutex> lk(mu_);
+        fn_ = nullptr;
+        idle_.wait(lk, [&] { return active_ == 0; });
+    }
+
+private:
+    HostPool() {
+        int width = std::min((int)std::thread::hardware_concurrency(), 16);
+        if (const char* e = getenv("OPAL_B200_HOST_THREADS")) width = std::max(1, std::min(atoi(e), 64));
+        const int n = std::max(0, width - 1);
+        for (int i = 0; i < n; i++) workers_.emplace_back([this] { loop(); });
+        for (auto& t : workers_) t.detach();
+    }
+    void loop() {
+        unsigned seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn;
+            std::atomic<char>* finished;
+            int parts;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return generation_ != seen && fn_ != nullptr; });
+                seen = generation_;
+                fn = fn_; finished = finished_; parts = parts_;
+                active_++;
+            }
+            for (;;) {
+                const int k = next_.fetch_add(1);
+                if (k >= parts) break;
+                (*fn)(k);
+                finished[k].store(1, std::memory_order_release);
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                active_--;
+            }
+            idle_.notify_all();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex jobMu_, mu_;
+    std::condition_variable cv_, idle_;
+    const std::function<void(int)>* fn_ = nullptr;
+    std::atomic<char>* finished_ = nullptr;
+    int parts_ = 0, active_ = 0;
+    unsigned generation_ = 0;
+    std::atomic<int> next_{0};
+};
+}  // namespace
 
 // Thread stride in the profile: a multiple of 4 words (16-byte aligned LDS.128) with an odd number of
 // 16-byte units, so the 8 lanes of a quarter-warp hit 8 different bank groups whatever their residues are.
@@ -267,30 +378,66 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
     return found;
 }
 
+// One thread per entry of the paired stream (pads included), so that a 35 000-residue target costs what 35 000
+// residues cost and not one warp's walk along it.  The pair an entry belongs to is found by bisection.
 static __global__ void pack_pairs_kernel(const uint8_t* residues, const long long* offsets, const int* lengths, int numTargets,
-                                  const long long* pairOffsets, int numPairs, uint16_t* pairStream, int* maxCode) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= numPairs) return;
-    const int a = 2 * warp, b = 2 * warp + 1;
-    const uint8_t* sa = residues + offsets[a];
-    const int Ta = lengths[a];
-    const uint8_t* sb = residues;
-    int Tb = 0;
-    if (b < numTargets) { sb = residues + offsets[b]; Tb = lengths[b]; }
-    uint16_t* out = pairStream + pairOffsets[warp];
-    uint32_t mx = 0;
-    for (int c = lane; c < Ta; c += 32) {
-        const uint32_t lo = (uint32_t)sa[c] + 1u;
-        const uint32_t hi = c < Tb ? (uint32_t)sb[c] + 1u : 0u;
-        mx = max(mx, max(lo, hi));
-        out[c] = (uint16_t)(lo | (hi << 8));
+                                  const long long* pairOffsets, int numPairs, long long entries, uint16_t* pairStream, int* maxCode) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t word = 0;
+    if (e < entries) {
+        int lo = 0, hi = numPairs;  // last pair whose first column is at or before e (entries before pair 0 are padding)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pairOffsets[mid] <= e) lo = mid; else hi = mid;
+        }
+        const long long c = e - pairOffsets[lo];
+        const int a = 2 * lo, b = 2 * lo + 1;
+        if (numPairs > 0 && c >= 0 && c < lengths[a]) {
+            word = (uint32_t)residues[offsets[a] + c] + 1u;
+            if (b < numTargets && c < lengths[b]) word |= ((uint32_t)residues[offsets[b] + c] + 1u) << 8;
+        }
+        pairStream[e] = (uint16_t)word;
     }
+    uint32_t mx = max(word & 0xffu, word >> 8);
     mx = __reduce_max_sync(0xffffffffu, mx);
-    if (lane == 0 && mx > 0) atomicMax(maxCode, (int)mx - 1);  // largest residue code seen
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(maxCode, (int)mx - 1);  // largest residue code seen
 }
 
 // ------------------------------------------------------------------ DeviceDb
 DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int device) {
+    return build(db, nullptr, lens, nullptr, n, device);
+}
+
+DeviceDb* DeviceDb::create_sorted(const unsigned char* residues, const int* sortedLens, const int* order, int n, int device) {
+    for (int p = 1; p < n; p++)
+        if (sortedLens[p] > sortedLens[p - 1]) { set_error("packed database is not sorted longest first"); return nullptr; }
+    if (order) {  // must be a permutation of 0..n-1
+        std::vector<char> seen((size_t)std::max(n, 1), 0);
+        for (int p = 0; p < n; p++) {
+            if (order[p] < 0 || order[p] >= n || seen[order[p]]) { set_error("packed database: order[] is not a permutation"); return nullptr; }
+            seen[order[p]] = 1;
+        }
+    }
+    return build(nullptr, residues, sortedLens, order, n, device);
+}
+
+bool DeviceDb::alloc_search_buffers() {
+    if (!stream_acquire(device_, &stream_) || !event_acquire(device_, &evStart_) || !event_acquire(device_, &evStop_) ||
+        !event_acquire(device_, &evFork_)) return false;
+    // One device block [score | endQ | endT | task list (2n)] and one pinned block [score | endQ | endT]: every
+    // stream operation has a fixed cost that exceeds the transfer itself at these sizes, so results come back in
+    // a single copy.
+    const size_t nWords = (size_t)std::max(n_, 1);
+    if (!device_alloc(device_, (void**)&dResults_, sizeof(int) * 5 * nWords)) return false;
+    if (!pinned_alloc((void**)&hResults_, sizeof(int) * 3 * nWords)) return false;
+    dScore_ = dResults_; dEndQ_ = dResults_ + nWords; dEndT_ = dResults_ + 2 * nWords; dTaskList_ = dResults_ + 3 * nWords;
+    hScore_ = hResults_; hEndQ_ = hResults_ + nWords; hEndT_ = hResults_ + 2 * nWords;
+    return true;
+}
+
+// Either `db` (n scattered sequences in caller order, lens[i]) or `packed` (contiguous, already sorted, lens[p],
+// order[p]) is given.  Returns with the upload in flight on the database's stream (see ensure_uploaded()).
+DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed, const int* lens, const int* order, int n, int device) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
         set_error("no usable CUDA device");
@@ -307,8 +454,8 @@ DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int
         if (di.major < 10) { set_error("device is not sm_100 or newer"); return false; }
         d->numSMs_ = di.numSMs;
         d->smemLimit_ = di.smemLimit;
-        if (!stream_acquire(device, &d->stream_) || !event_acquire(device, &d->evStart_) || !event_acquire(device, &d->evStop_) ||
-            !event_acquire(device, &d->evFork_)) return false;
+        PhaseTrace trace("build");
+        trace.mark("setup");
 
         // ---- sort by length, longest first (counting sort; stable in caller order)
         int maxLen = 0;
@@ -318,7 +465,9 @@ DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int
         }
         d->order_.resize(n);
         d->pos_.resize(n);
-        if (maxLen <= (1 << 22)) {
+        if (packed) {
+            for (int p = 0; p < n; p++) d->order_[p] = order ? order[p] : p;
+        } else if (maxLen <= (1 << 22)) {
             std::vector<int> start(maxLen + 2, 0);
             for (int i = 0; i < n; i++) start[maxLen - lens[i] + 1]++;
             for (int k = 1; k <= maxLen + 1; k++) start[k] += start[k - 1];
@@ -327,90 +476,158 @@ DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int
             for (int i = 0; i < n; i++) d->order_[i] = i;
             std::stable_sort(d->order_.begin(), d->order_.end(), [&](int a, int b) { return lens[a] > lens[b]; });
         }
+        // Residues are stored in the order they are copied in -- caller order for scattered sequences (sequential
+        // reads of the caller's memory, runs of adjacent sequences merge into one memcpy), sorted order for a
+        // packed database -- and offsets_[p] says where sorted position p lives.  Nothing needs the sorted
+        // sequences to be adjacent: the 16-bit kernels stream the paired layout built on the device below.
+        std::vector<long long> copyOff((size_t)n + 1);  // in copy order
+        long long total = 0;
+        for (int i = 0; i < n; i++) { copyOff[i] = total; total += lens[i]; }
+        copyOff[n] = total;
         d->sortedLen_.resize(n);
         d->offsets_.resize((size_t)n + 1);
-        long long total = 0;
         for (int p = 0; p < n; p++) {
             const int i = d->order_[p];
             d->pos_[i] = p;
-            d->sortedLen_[p] = lens[i];
-            d->offsets_[p] = total;
-            total += lens[i];
+            d->sortedLen_[p] = packed ? lens[p] : lens[i];
+            d->offsets_[p] = packed ? copyOff[p] : copyOff[i];
         }
         d->offsets_[n] = total;
         d->totalResidues_ = total;
+        trace.mark("sort");
+        if (!d->alloc_search_buffers()) return false;
+        trace.mark("buffers");
 
-        // ---- gather into pinned staging, in sorted order, on several host threads
-        const size_t bytes = (size_t)total + 64;
-        uint8_t* staging = nullptr;
-        if (!pinned_alloc((void**)&staging, bytes)) return false;
-        memset(staging + total, 0, 64);
-        // host threads only pay off for large databases (spawning them costs more than copying a few MB)
-        int nThreads = total < (32 << 20) ? 1 : (int)std::min<long long>(std::max(1u, std::thread::hardware_concurrency()), total / (8 << 20));
-        nThreads = std::max(1, std::min(nThreads, 32));
-        auto gather = [&](int lo, int hi) {
-            for (int p = lo; p < hi; p++)
-                if (d->sortedLen_[p] > 0) memcpy(staging + d->offsets_[p], db[d->order_[p]], (size_t)d->sortedLen_[p]);
-        };
-        if (nThreads == 1) gather(0, n);
-        else {
-            std::vector<std::thread> th;
-            int lo = 0;
-            for (int k = 0; k < nThreads; k++) {
-                const long long target = total * (k + 1) / nThreads;
-                int hi = (k == nThreads - 1) ? n : (int)(std::upper_bound(d->offsets_.begin(), d->offsets_.begin() + n, target) - d->offsets_.begin());
-                hi = std::max(hi, lo);
-                th.emplace_back(gather, lo, hi);
-                lo = hi;
-            }
-            for (auto& t : th) t.join();
-        }
-        if (!device_alloc(device, (void**)&d->dResidues_, bytes)) return false;
-        CUDA_TRY(cudaMemcpyAsync(d->dResidues_, staging, bytes, cudaMemcpyHostToDevice, d->stream_));
-        if (!device_alloc(device, (void**)&d->dOffsets_, sizeof(long long) * ((size_t)n + 1))) return false;
-        CUDA_TRY(cudaMemcpyAsync(d->dOffsets_, d->offsets_.data(), sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, d->stream_));
-        const size_t nInts = sizeof(int) * (size_t)std::max(n, 1);
-        if (!device_alloc(device, (void**)&d->dLengths_, nInts)) return false;
-        CUDA_TRY(cudaMemcpyAsync(d->dLengths_, d->sortedLen_.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, d->stream_));
-        if (!device_alloc(device, (void**)&d->dScore_, nInts)) return false;
-        if (!device_alloc(device, (void**)&d->dEndQ_, nInts)) return false;
-        if (!device_alloc(device, (void**)&d->dEndT_, nInts)) return false;
-        if (!device_alloc(device, (void**)&d->dTaskList_, 2 * nInts)) return false;
-        if (!device_alloc(device, (void**)&d->dCounters_, sizeof(int) * 256)) return false;
-        if (!pinned_alloc((void**)&d->hScore_, nInts)) return false;
-        if (!pinned_alloc((void**)&d->hEndQ_, nInts)) return false;
-        if (!pinned_alloc((void**)&d->hEndT_, nInts)) return false;
-        // ---- paired stream: [32 zeros][pair 0 columns][32 zeros][pair 1 columns] ... built on the device
+        // ---- one pinned block [offsets | pair offsets | lengths | max code | residues], one upload.  (Every stream
+        // operation costs tens of microseconds on its own here, far more than its share of a few MB, so the
+        // database goes up in a single copy once the gather is complete.)  The residues part stays as the host
+        // copy the alignment stage replays against.  Paired stream: [32 zeros][pair 0 columns][32 zeros][pair 1 ...].
         d->numPairs_ = (n + 1) / 2;
-        std::vector<long long> pairOff((size_t)std::max(d->numPairs_, 1));
+        const size_t nOff = (size_t)n + 1, nPair = (size_t)std::max(d->numPairs_, 1), nLen = (size_t)std::max(n, 1);
+        const size_t indexBytes = (sizeof(long long) * (nOff + nPair) + sizeof(int) * (nLen + 1) + 255) / 256 * 256;
+        const size_t bytes = indexBytes + (size_t)total + 64;
+        if (!pinned_alloc((void**)&d->hBlock_, bytes)) return false;
+        if (!device_alloc(device, (void**)&d->dBlock_, bytes)) return false;
+        long long* hOff = reinterpret_cast<long long*>(d->hBlock_);
+        long long* hPair = hOff + nOff;
+        int* hLen = reinterpret_cast<int*>(hPair + nPair);
+        d->hResidues_ = d->hBlock_ + indexBytes;
+        d->dOffsets_ = reinterpret_cast<long long*>(d->dBlock_);
+        d->dPairOffsets_ = d->dOffsets_ + nOff;
+        d->dLengths_ = reinterpret_cast<int*>(d->dPairOffsets_ + nPair);
+        d->dMaxCode_ = d->dLengths_ + nLen;
+        d->dResidues_ = d->dBlock_ + indexBytes;
+        memcpy(hOff, d->offsets_.data(), sizeof(long long) * nOff);
+        hLen[0] = 0;
+        if (n > 0) memcpy(hLen, d->sortedLen_.data(), sizeof(int) * (size_t)n);
+        hLen[nLen] = 0;  // max code, raised by the pairing kernel
         long long entries = 32;
-        for (int p = 0; p < d->numPairs_; p++) { pairOff[p] = entries; entries += d->sortedLen_[2 * p] + 32; }
+        hPair[0] = 32;
+        for (int p = 0; p < d->numPairs_; p++) { hPair[p] = entries; entries += d->sortedLen_[2 * p] + 32; }
         entries += 64;
+        uint8_t* staging = d->hResidues_;
+        memset(staging + total, 0, 64);
+        // Parts of about equal residue count, cut at sequence boundaries; each is uploaded as soon as it and all
+        // parts before it are staged, so the copy engine runs behind the host copy.  Small databases are staged by
+        // the calling thread alone: the DMA engine reads lines that sit dirty in ONE core's cache at full speed,
+        // and several times slower when they are spread over the caches of many cores (measured: 4.5 MB in 96 us
+        // after a 1-thread copy, 680 us after a 16-thread one).  Large databases do not fit in any cache and
+        // take the host pool.
+        HostPool& pool = HostPool::get();
+        const bool threaded = total >= (64LL << 20) && pool.width() > 1;
+        const long long partBytes = threaded ? (8 << 20) : (1 << 20);
+        const int parts = (int)std::max<long long>(1, std::min<long long>(total / partBytes, 4096));
+        std::vector<int> cut((size_t)parts + 1, n);
+        cut[0] = 0;
+        for (int k = 1; k < parts; k++) {
+            const long long target = total * k / parts;
+            cut[k] = std::max(cut[k - 1], (int)(std::lower_bound(copyOff.begin(), copyOff.begin() + n, target) - copyOff.begin()));
+        }
+        auto stage = [&](int k) {
+            const int lo = cut[k], hi = cut[k + 1];
+            if (lo >= hi) return;
+            if (packed) { memcpy(staging + copyOff[lo], packed + copyOff[lo], (size_t)(copyOff[hi] - copyOff[lo])); return; }
+            int j = lo;
+            while (j < hi) {  // one memcpy per run of sequences that are adjacent in the caller's memory
+                int e = j + 1;
+                while (e < hi && db[e] == db[e - 1] + lens[e - 1]) e++;
+                const long long len = copyOff[e] - copyOff[j];
+                if (len > 0) memcpy(staging + copyOff[j], db[j], (size_t)len);
+                j = e;
+            }
+        };
+        cudaError_t copyError = cudaSuccess;
+        size_t uploaded = 0;  // bytes of the block already handed to the copy engine
+        auto upload = [&](int k) {
+            const size_t end = k == parts - 1 ? bytes : indexBytes + (size_t)copyOff[cut[k + 1]];
+            for (size_t at = uploaded; at < end; at += (size_t)1 << 30) {
+                const cudaError_t ce = cudaMemcpyAsync(d->dBlock_ + at, d->hBlock_ + at, std::min(end - at, (size_t)1 << 30), cudaMemcpyHostToDevice, d->stream_);
+                if (ce != cudaSuccess) copyError = ce;
+            }
+            uploaded = std::max(uploaded, end);
+        };
+        trace.mark("index");
+        if (trace.on) CUDA_TRY(cudaEventRecord(d->evStart_, d->stream_));
+        if (threaded) pool.run(parts, stage, upload);
+        else for (int k = 0; k < parts; k++) { stage(k); upload(k); }
+        CUDA_TRY(copyError);
+        trace.mark("stage+issue");
+        if (trace.on) CUDA_TRY(cudaEventRecord(d->evFork_, d->stream_));
         if (!device_alloc(device, (void**)&d->dPairStream_, sizeof(uint16_t) * (size_t)entries)) return false;
-        if (!device_alloc(device, (void**)&d->dPairOffsets_, sizeof(long long) * pairOff.size())) return false;
-        if (!device_alloc(device, (void**)&d->dMaxCode_, sizeof(int))) return false;
-        CUDA_TRY(cudaMemsetAsync(d->dPairStream_, 0, sizeof(uint16_t) * (size_t)entries, d->stream_));
-        CUDA_TRY(cudaMemsetAsync(d->dMaxCode_, 0, sizeof(int), d->stream_));
-        CUDA_TRY(cudaMemcpyAsync(d->dPairOffsets_, pairOff.data(), sizeof(long long) * pairOff.size(), cudaMemcpyHostToDevice, d->stream_));
-        if (d->numPairs_ > 0) {
-            pack_pairs_kernel<<<(d->numPairs_ + 7) / 8, 256, 0, d->stream_>>>(d->dResidues_, d->dOffsets_, d->dLengths_, n, d->dPairOffsets_,
-                                                                             d->numPairs_, d->dPairStream_, d->dMaxCode_);
+        if (!pinned_alloc((void**)&d->hMaxCode_, sizeof(int))) return false;
+        {
+            const long long blocks = (entries + 255) / 256;
+            pack_pairs_kernel<<<(unsigned)blocks, 256, 0, d->stream_>>>(d->dResidues_, d->dOffsets_, d->dLengths_, n, d->dPairOffsets_,
+                                                                        d->numPairs_, entries, d->dPairStream_, d->dMaxCode_);
             CUDA_TRY(cudaGetLastError());
         }
-        CUDA_TRY(cudaMemcpyAsync(&d->maxCode_, d->dMaxCode_, sizeof(int), cudaMemcpyDeviceToHost, d->stream_));
-        CUDA_TRY(cudaStreamSynchronize(d->stream_));
-        pinned_release(staging);
-        return true;
+        CUDA_TRY(cudaMemcpyAsync(d->hMaxCode_, d->dMaxCode_, sizeof(int), cudaMemcpyDeviceToHost, d->stream_));
+        if (trace.on) CUDA_TRY(cudaEventRecord(d->evStop_, d->stream_));
+        trace.mark("issue");
+        return true;  // upload still in flight: see ensure_uploaded()
     }();
     return ok ? d : fail();
 }
 
+bool DeviceDb::ensure_uploaded() {
+    if (uploaded_) return true;
+    CUDA_TRY(cudaSetDevice(device_));
+    CUDA_TRY(cudaStreamSynchronize(stream_));
+    if (getenv("OPAL_B200_TRACE") && ownsDb_) {
+        float copies = 0.f, pack = 0.f;
+        if (cudaEventElapsedTime(&copies, evStart_, evFork_) == cudaSuccess && cudaEventElapsedTime(&pack, evFork_, evStop_) == cudaSuccess)
+            fprintf(stderr, "[opal-b200] upload on the device: copies %.0f us, pairing %.0f us\n", copies * 1e3, pack * 1e3);
+    }
+    maxCode_ = hMaxCode_ ? *hMaxCode_ : 0;
+    uploaded_ = true;
+    return true;
+}
+
+// A search context over the same resident database: own stream, events, result and scratch buffers.
+DeviceDb* DeviceDb::clone_context() {
+    if (!ensure_uploaded()) return nullptr;
+    DeviceDb* c = new DeviceDb();
+    c->ownsDb_ = false; c->uploaded_ = true;
+    c->device_ = device_; c->n_ = n_; c->numSMs_ = numSMs_; c->smemLimit_ = smemLimit_; c->totalResidues_ = totalResidues_;
+    c->order_ = order_; c->pos_ = pos_; c->sortedLen_ = sortedLen_; c->offsets_ = offsets_;
+    c->hResidues_ = hResidues_; c->dResidues_ = dResidues_; c->dOffsets_ = dOffsets_; c->dLengths_ = dLengths_;
+    c->dPairStream_ = dPairStream_; c->dPairOffsets_ = dPairOffsets_; c->numPairs_ = numPairs_; c->maxCode_ = maxCode_;
+    if (cudaSetDevice(device_) != cudaSuccess || !c->alloc_search_buffers()) { delete c; return nullptr; }
+    return c;
+}
+
 DeviceDb::~DeviceDb() {
     cudaSetDevice(device_);
+    for (DeviceDb* c : contexts_) delete c;
     if (stream_) cudaStreamSynchronize(stream_);
-    void* dev[] = {dResidues_, dOffsets_, dLengths_, dScore_, dEndQ_, dEndT_, dTaskList_, dCounters_, dBndH_, dBndF_, dQuery_, dMatrix_, dPairStream_, dPairOffsets_, dMaxCode_};
-    for (void* p : dev) device_release(device_, p);
-    pinned_release(hScore_); pinned_release(hEndQ_); pinned_release(hEndT_);
+    void* own[] = {dResults_, dArgs_, dBndH_, dBndF_};
+    for (void* p : own) device_release(device_, p);
+    if (ownsDb_) {
+        void* shared[] = {dBlock_, dPairStream_};
+        for (void* p : shared) device_release(device_, p);
+        pinned_release(hBlock_); pinned_release(hMaxCode_);
+    }
+    pinned_release(hResults_); pinned_release(hArgs_);
     event_release(device_, evStart_); event_release(device_, evStop_); event_release(device_, evFork_);
     for (cudaStream_t st : auxStreams_) { cudaStreamSynchronize(st); stream_release(device_, st); }
     for (cudaEvent_t e : auxEvents_) event_release(device_, e);
@@ -556,9 +773,11 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
 int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int>*>>& classes, const unsigned char* dQuery,
                           const int* dMatrix, int Q, int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot) {
     std::vector<Group> groups;
+    PhaseTrace trace("run_classes");
     for (auto& c : classes)
         if (!plan_class(c.first, *c.second, Q, A, mode, &groups)) return OPAL_B200_ERR_CUDA;
     if (groups.empty()) return 0;
+    trace.mark("plan");
     stats_.groups = (int)groups.size();
     // Concurrent groups own disjoint SMs (grids are persistent, one block per SM, and every block must be
     // resident from the start because first tasks are assigned statically).  Small groups -- the latency
@@ -594,6 +813,11 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
                     g.g.warpsPerPartition, g.g.passes, g.maxBlocks, g.estCycles / 1e3);
     auto body = [&]() -> bool {
         size_t listOffset = 0;
+        // create() returns with the upload in flight; planning above ran beside it.  The residue codes are
+        // validated here, before anything indexes the profile with them.
+        if (!ensure_uploaded()) return false;
+        trace.mark("upload-wait");
+        if (maxCode_ >= A) { set_error("database holds residue codes >= alphabetLength"); return false; }
         if (!startRecorded_) { CUDA_TRY(cudaEventRecord(evStart_, stream_)); startRecorded_ = true; }  // planning is host work: keep it outside the device window
         if (groups.size() > 1) CUDA_TRY(cudaEventRecord(evFork_, stream_));
         for (size_t gi = 0; gi < groups.size(); gi++) {
@@ -623,6 +847,7 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
 int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const int* matrix, int A, int wantEnd, int mode,
                      const unsigned char* skip, int* scores, int* endQ, int* endT, float* deviceMs) {
     stats_ = SearchStats();
+    PhaseTrace trace("search");
     if (deviceMs) *deviceMs = 0.f;
     if (mode != kModeNW && mode != kModeHW && mode != kModeOV && mode != kModeSW) return OPAL_B200_ERR_MODE;
     if (A <= 0 || A > 254) { set_error("alphabetLength must be in [1, 254]"); return OPAL_B200_ERR_CUDA; }
@@ -641,7 +866,6 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
     const bool args32 = absP < (1 << 28) && gapMax < (1 << 28);
     if (!args32) return OPAL_B200_ERR_OVERFLOW;  // beyond the widths this engine carries (documented deviation)
 
-    if (maxCode_ >= A) { set_error("database holds residue codes >= alphabetLength"); return OPAL_B200_ERR_CUDA; }
     for (int r = 0; r < Q; r++)
         if (query[r] >= A) { set_error("query holds residue codes >= alphabetLength"); return OPAL_B200_ERR_CUDA; }
 
@@ -654,6 +878,7 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
         return lo <= lim && hi <= lim;
     };
     std::vector<int> list16, list32;
+    (args16 ? list16 : list32).reserve((size_t)n_);
     bool touched = false;
     for (int p = 0; p < n_; p++) {
         const int i = order_[p];
@@ -680,6 +905,7 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
         }
     }
     if (!touched) return 0;
+    trace.mark("route");
     // The 16-bit class works on whole pairs (sorted targets 2p, 2p+1) and the two classes of NW/HW/OV run
     // concurrently, so a pair is never split between them: if one member needs 32 bits, both go there.
     if (!isSW && !list32.empty() && !list16.empty()) {
@@ -700,26 +926,31 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
     int rc = 0;
     auto body = [&]() -> bool {
         CUDA_TRY(cudaSetDevice(device_));
-        if ((size_t)Q + 16 > queryCapacity_) {
-            device_release(device_, dQuery_); dQuery_ = nullptr;
-            queryCapacity_ = std::max<size_t>(4096, 2 * ((size_t)Q + 16));
-            if (!device_alloc(device_, (void**)&dQuery_, queryCapacity_)) return false;
+        // launch counters (zeroed), score matrix and query travel in one pinned block, one copy
+        const size_t countersBytes = sizeof(int) * 256, matrixBytes = (sizeof(int) * (size_t)A * A + 255) / 256 * 256;
+        const size_t argsBytes = countersBytes + matrixBytes + (size_t)Q + 16;
+        if (argsBytes > argsCapacity_) {
+            device_release(device_, dArgs_); dArgs_ = nullptr;
+            pinned_release(hArgs_); hArgs_ = nullptr;
+            argsCapacity_ = std::max<size_t>(8192, 2 * argsBytes);
+            if (!device_alloc(device_, (void**)&dArgs_, argsCapacity_) || !pinned_alloc((void**)&hArgs_, argsCapacity_)) { argsCapacity_ = 0; return false; }
         }
-        if (!dMatrix_ && !device_alloc(device_, (void**)&dMatrix_, sizeof(int) * 256 * 256)) return false;
-        dQuery = dQuery_; dMatrix = dMatrix_;
-        CUDA_TRY(cudaMemcpyAsync(dQuery, query, (size_t)Q, cudaMemcpyHostToDevice, stream_));
-        CUDA_TRY(cudaMemcpyAsync(dMatrix, matrix, sizeof(int) * A * A, cudaMemcpyHostToDevice, stream_));
-        CUDA_TRY(cudaMemsetAsync(dCounters_, 0, sizeof(int) * 256, stream_));
+        memset(hArgs_, 0, countersBytes);
+        memcpy(hArgs_ + countersBytes, matrix, sizeof(int) * (size_t)A * A);
+        memcpy(hArgs_ + countersBytes + matrixBytes, query, (size_t)Q);
+        dCounters_ = reinterpret_cast<int*>(dArgs_);
+        dMatrix = reinterpret_cast<int*>(dArgs_ + countersBytes);
+        dQuery = dArgs_ + countersBytes + matrixBytes;
+        CUDA_TRY(cudaMemcpyAsync(dArgs_, hArgs_, argsBytes, cudaMemcpyHostToDevice, stream_));
         int slot = 0;
         startRecorded_ = false;
         auto fetch = [&]() -> bool {
-            const size_t nInts = sizeof(int) * (size_t)n_;
-            CUDA_TRY(cudaMemcpyAsync(hScore_, dScore_, nInts, cudaMemcpyDeviceToHost, stream_));
-            if (wantEnd) {
-                CUDA_TRY(cudaMemcpyAsync(hEndQ_, dEndQ_, nInts, cudaMemcpyDeviceToHost, stream_));
-                CUDA_TRY(cudaMemcpyAsync(hEndT_, dEndT_, nInts, cudaMemcpyDeviceToHost, stream_));
-            }
+            // [score | endQ | endT] are adjacent on both sides: one copy
+            const size_t nWords = (size_t)std::max(n_, 1);
+            CUDA_TRY(cudaMemcpyAsync(hResults_, dResults_, sizeof(int) * (wantEnd ? 3 : 1) * nWords, cudaMemcpyDeviceToHost, stream_));
+            trace.mark("launch");
             CUDA_TRY(cudaStreamSynchronize(stream_));
+            trace.mark("wait");
             return true;
         };
         auto publish = [&](const std::vector<int>& list, std::vector<int>* overflowed) {
@@ -760,12 +991,64 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
             if (!fetch()) return false;
             publish(list32, nullptr);
         }
+        trace.mark("publish");
         if (deviceMs && startRecorded_) CUDA_TRY(cudaEventElapsedTime(deviceMs, evStart_, evStop_));
         return true;
     };
     const bool okb = body();
     if (!okb) return OPAL_B200_ERR_CUDA;
     return rc;
+}
+
+int DeviceDb::search_batch(int numQueries, const unsigned char* const* queries, const int* queryLengths, int Go, int Ge,
+                           const int* matrix, int A, int wantEnd, int mode, int* scores, int* endQ, int* endT, int inFlight,
+                           float* batchMs) {
+    if (batchMs) *batchMs = 0.f;
+    if (numQueries <= 0) return 0;
+    const int K = std::max(1, std::min(std::min(inFlight, numQueries), 8));
+    if (cudaSetDevice(device_) != cudaSuccess) { set_error("cudaSetDevice failed"); return OPAL_B200_ERR_CUDA; }
+    while ((int)contexts_.size() < K - 1) {
+        DeviceDb* c = clone_context();
+        if (!c) return OPAL_B200_ERR_CUDA;
+        contexts_.push_back(c);
+    }
+    if (!ensure_uploaded()) return OPAL_B200_ERR_CUDA;
+    cudaEvent_t evBatch = nullptr;
+    if (!event_acquire(device_, &evBatch)) return OPAL_B200_ERR_CUDA;
+    if (cudaEventRecord(evBatch, stream_) != cudaSuccess) { event_release(device_, evBatch); set_error("cudaEventRecord failed"); return OPAL_B200_ERR_CUDA; }
+    std::atomic<int> next(0);
+    std::vector<int> rcs((size_t)K, 0);
+    std::vector<std::string> errors((size_t)K);
+    std::vector<float> lastStop((size_t)K, 0.f);
+    std::vector<int> launches((size_t)K, 0), reruns((size_t)K, 0);
+    auto worker = [&](int k) {
+        DeviceDb* ctx = k == 0 ? this : contexts_[k - 1];
+        for (;;) {
+            const int q = next.fetch_add(1);
+            if (q >= numQueries) break;
+            const size_t base = (size_t)q * (size_t)n_;
+            const int rc = ctx->search(queries[q], queryLengths[q], Go, Ge, matrix, A, wantEnd, mode, nullptr, scores + base,
+                                       endQ ? endQ + base : nullptr, endT ? endT + base : nullptr, nullptr);
+            if (rc) { rcs[k] = rc; errors[k] = last_error(); break; }
+            launches[k] += ctx->stats_.kernelLaunches; reruns[k] += ctx->stats_.rerun32;
+            float ms = 0.f;
+            if (ctx->startRecorded_ && cudaEventElapsedTime(&ms, evBatch, ctx->evStop_) == cudaSuccess) lastStop[k] = std::max(lastStop[k], ms);
+        }
+    };
+    if (K == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (int k = 1; k < K; k++) th.emplace_back(worker, k);
+        worker(0);
+        for (auto& t : th) t.join();
+    }
+    event_release(device_, evBatch);
+    for (int k = 0; k < K; k++)
+        if (rcs[k]) { set_error(errors[k]); return rcs[k]; }
+    if (batchMs) *batchMs = *std::max_element(lastStop.begin(), lastStop.end());
+    stats_.kernelLaunches = stats_.rerun32 = 0;  // batch totals
+    for (int k = 0; k < K; k++) { stats_.kernelLaunches += launches[k]; stats_.rerun32 += reruns[k]; }
+    return 0;
 }
 
 // ------------------------------------------------------------------ DPX roofline probe

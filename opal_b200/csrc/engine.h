@@ -29,6 +29,10 @@ struct SearchStats {
     int kernelLaunches = 0, rerun32 = 0, G = 0, R = 0, passes = 0, warpsPerPartition = 0, groups = 0;
 };
 
+// Device memory from the per-device block cache (engine.cu): recycled, not returned to the driver.
+bool device_alloc(int device, void** p, size_t bytes);
+void device_release(int device, void* p);
+
 void set_error(const std::string& msg);
 const char* last_error();
 
@@ -36,7 +40,19 @@ const char* last_error();
 class DeviceDb {
 public:
     static DeviceDb* create(unsigned char* const* db, int n, const int* lens, int device);
+    // Database that is already packed: residues contiguous, longest sequence first; order[p] = caller index of
+    // sorted position p (NULL = identity).  This is the in-memory form of the on-disk format (cli/packed_db.h).
+    static DeviceDb* create_sorted(const unsigned char* residues, const int* sortedLens, const int* order, int n, int device);
     ~DeviceDb();
+
+    // Several queries against the resident database, up to `inFlight` of them on the device at a time (each on a
+    // search context of its own: streams, result and scratch buffers), so that the tail of one query overlaps the
+    // bulk of the next and host-side planning / publishing overlaps kernels.  Outputs are [query][caller index].
+    int search_batch(int numQueries, const unsigned char* const* queries, const int* queryLengths, int Go, int Ge,
+                     const int* matrix, int A, int wantEnd, int mode, int* scores, int* endQ, int* endT, int inFlight,
+                     float* batchMs);
+    // Blocks until the upload issued by create() has finished (create() returns with it in flight).
+    bool ensure_uploaded();
 
     // Score / score+end for every non-skipped target; outputs in caller order (-1 = unset).
     int search(const unsigned char* query, int Q, int Go, int Ge, const int* matrix, int A, int wantEnd, int mode,
@@ -54,9 +70,13 @@ public:
     const long long* d_offsets() const { return dOffsets_; }
     const std::vector<long long>& offsets() const { return offsets_; }
     const std::vector<int>& sorted_lengths() const { return sortedLen_; }
+    const uint8_t* h_residues() const { return hResidues_; }  // pinned host copy, sorted order
 
 private:
     DeviceDb() {}
+    static DeviceDb* build(unsigned char* const* db, const unsigned char* packed, const int* lens, const int* order, int n, int device);
+    DeviceDb* clone_context();
+    bool alloc_search_buffers();
     struct Group;
     bool plan_class(int type, const std::vector<int>& list, int Q, int A, int mode, std::vector<Group>* groups);
     bool launch_group(const Group& grp, int* taskListDevice, cudaStream_t stream, const unsigned char* dQuery, const int* dMatrix,
@@ -69,19 +89,23 @@ private:
     long long totalResidues_ = 0;
     std::vector<int> order_, pos_, sortedLen_;
     std::vector<long long> offsets_;
+    bool ownsDb_ = true, uploaded_ = false;  // search contexts made by clone_context() borrow the database arrays
+    std::vector<DeviceDb*> contexts_;
+    uint8_t* hResidues_ = nullptr;
     uint8_t* dResidues_ = nullptr;
     long long* dOffsets_ = nullptr;
     int* dLengths_ = nullptr;
-    int *dScore_ = nullptr, *dEndQ_ = nullptr, *dEndT_ = nullptr, *dTaskList_ = nullptr, *dCounters_ = nullptr;
+    int *dResults_ = nullptr, *hResults_ = nullptr;  // [score | endQ | endT | task list] device block, [score | endQ | endT] pinned
+    int *dScore_ = nullptr, *dEndQ_ = nullptr, *dEndT_ = nullptr, *dTaskList_ = nullptr, *dCounters_ = nullptr;  // views
     uint32_t *dBndH_ = nullptr, *dBndF_ = nullptr;
     uint16_t* dPairStream_ = nullptr;
     long long* dPairOffsets_ = nullptr;
-    int* dMaxCode_ = nullptr;
+    int *dMaxCode_ = nullptr, *hMaxCode_ = nullptr;
+    unsigned char *hBlock_ = nullptr, *dBlock_ = nullptr;  // offsets | pair offsets | lengths | max code | residues (pinned / device)
     int numPairs_ = 0, maxCode_ = 0;
-    unsigned char* dQuery_ = nullptr;
-    int* dMatrix_ = nullptr;
-    size_t queryCapacity_ = 0;
-    int *hScore_ = nullptr, *hEndQ_ = nullptr, *hEndT_ = nullptr;  // pinned
+    unsigned char *dArgs_ = nullptr, *hArgs_ = nullptr;  // launch counters | score matrix | query (device / pinned)
+    size_t argsCapacity_ = 0;
+    int *hScore_ = nullptr, *hEndQ_ = nullptr, *hEndT_ = nullptr;  // views into hResults_
     cudaStream_t stream_ = nullptr;
     cudaEvent_t evStart_ = nullptr, evStop_ = nullptr, evFork_ = nullptr;
     std::vector<cudaStream_t> auxStreams_;

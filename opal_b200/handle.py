@@ -10,7 +10,7 @@ import os
 
 import numpy as np
 
-from .capi import MODES, OpalCLibrary, SequenceDB
+from .capi import MODES, OpalCLibrary, SequenceDB, new_results, result_pointers
 
 LIB_PATH = os.environ.get("OPAL_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libopal_b200.so")
 
@@ -28,6 +28,12 @@ class OpalB200(OpalCLibrary):
         L.opalb200_last_error.restype = ctypes.c_char_p
         L.opalb200_db_create.argtypes = [vp, ci, vp, ci]
         L.opalb200_db_create.restype = vp
+        L.opalb200_db_create_sorted.argtypes = [vp, vp, vp, ci, ci]
+        L.opalb200_db_create_sorted.restype = vp
+        L.opalb200_db_search_batch.argtypes = [vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, vp, vp, vp, ci, vp]
+        L.opalb200_db_search_batch.restype = ci
+        L.opalb200_db_search_results.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp, ci, ci]
+        L.opalb200_db_search_results.restype = ci
         L.opalb200_db_destroy.argtypes = [vp]
         L.opalb200_db_destroy.restype = None
         L.opalb200_db_length.argtypes = [vp]
@@ -52,6 +58,18 @@ class OpalB200(OpalCLibrary):
         if not h:
             raise RuntimeError("opalb200_db_create failed: " + self.last_error())
         return ResidentDb(self, h, len(db))
+
+    def create_db_sorted(self, residues, sorted_lengths, order=None, device=0):
+        """opalb200_db_create_sorted: a database that is already packed (longest first, contiguous)."""
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        lens = np.ascontiguousarray(sorted_lengths, dtype=np.int32)
+        buf = residues if residues.size else np.zeros(1, dtype=np.uint8)
+        order_arr = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+        h = self.lib.opalb200_db_create_sorted(buf.ctypes.data, lens.ctypes.data,
+                                               None if order_arr is None else order_arr.ctypes.data, int(lens.size), int(device))
+        if not h:
+            raise RuntimeError("opalb200_db_create_sorted failed: " + self.last_error())
+        return ResidentDb(self, h, int(lens.size))
 
     def measure_dpx_peak(self, device=0):
         ips, ms = ctypes.c_double(0), ctypes.c_float(0)
@@ -83,6 +101,41 @@ class ResidentDb:
             int(alphabet_length), int(search_type), int(mode), None if skp is None else skp.ctypes.data,
             sc.ctypes.data, eq.ctypes.data, et.ctypes.data, ctypes.byref(ms))
         return rc, sc, eq, et, float(ms.value)
+
+    def search_batch(self, queries, gap_open, gap_ext, score_matrix, alphabet_length, search_type, mode, in_flight=3):
+        """opalb200_db_search_batch. Returns (rc, scores[nq, n], endQuery, endTarget, batch_ms)."""
+        qs = [np.ascontiguousarray(q, dtype=np.uint8) for q in queries]
+        qs = [q if q.size else np.zeros(1, dtype=np.uint8) for q in qs]
+        nq = len(qs)
+        ptrs = np.array([q.ctypes.data for q in qs], dtype=np.uint64)
+        qlens = np.array([len(q) for q in queries], dtype=np.int32)
+        sm = np.ascontiguousarray(score_matrix, dtype=np.int32).ravel()
+        sc = np.zeros((nq, self.n), dtype=np.int32)
+        eq = np.full((nq, self.n), -1, dtype=np.int32)
+        et = np.full((nq, self.n), -1, dtype=np.int32)
+        ms = ctypes.c_float(0)
+        if isinstance(mode, str):
+            mode = MODES[mode]
+        rc = self.eng.lib.opalb200_db_search_batch(
+            self.handle, nq, ptrs.ctypes.data, qlens.ctypes.data, int(gap_open), int(gap_ext), sm.ctypes.data,
+            int(alphabet_length), int(search_type), int(mode), sc.ctypes.data, eq.ctypes.data, et.ctypes.data,
+            int(in_flight), ctypes.byref(ms))
+        return rc, sc, eq, et, float(ms.value)
+
+    def search_results(self, query, gap_open, gap_ext, score_matrix, alphabet_length, search_type, mode, results=None):
+        """opalb200_db_search_results: opalSearchDatabase's records against the resident database. Returns (rc, results)."""
+        query = np.ascontiguousarray(query, dtype=np.uint8)
+        sm = np.ascontiguousarray(score_matrix, dtype=np.int32).ravel()
+        if results is None:
+            results = new_results(self.n)
+        rp = result_pointers(results)
+        qbuf = query if query.size else np.zeros(1, dtype=np.uint8)
+        if isinstance(mode, str):
+            mode = MODES[mode]
+        rc = self.eng.lib.opalb200_db_search_results(
+            self.handle, qbuf.ctypes.data, int(query.size), int(gap_open), int(gap_ext), sm.ctypes.data,
+            int(alphabet_length), rp.ctypes.data, int(search_type), int(mode))
+        return rc, results
 
     def last_stats(self):
         v = [ctypes.c_int(0) for _ in range(7)]

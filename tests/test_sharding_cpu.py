@@ -76,7 +76,8 @@ def test_c_abi_exports_every_declared_symbol():
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         declared |= set(re.findall(r"\b(opal[A-Za-z0-9_]+)\s*\(", text))
     assert {"opalSearchDatabase", "opalSearchDatabaseCharSW", "opalSearchDatabaseRescore", "opalInitSearchResult",
-            "opalSearchResultIsEmpty", "opalSearchResultSetScore", "opalb200_db_create", "opalb200_db_search"} <= declared
+            "opalSearchResultIsEmpty", "opalSearchResultSetScore", "opalb200_db_create", "opalb200_db_search",
+            "opalb200_db_create_sorted", "opalb200_db_search_batch", "opalb200_db_search_results"} <= declared
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared in include/ but not exported"
 
