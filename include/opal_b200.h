@@ -81,6 +81,19 @@ int opalb200_db_search_results(OpalB200Db* handle, const unsigned char query[], 
                                int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength,
                                struct OpalSearchResult* results[], int searchType, int mode);
 
+/*
+ * Score -> top-k -> alignment in one call on the resident database (BASELINE configs[3]: "SCORE pass, take the
+ * top 1000, ALIGNMENT on those"): a score + end search over every sequence, selection of the k best (score
+ * descending, ties by caller index ascending) and, for searchType OPAL_SEARCH_ALIGNMENT, start location and
+ * alignment of just those k -- nothing is re-uploaded and nothing is scored twice, which is what the two
+ * opalSearchDatabase calls of the reference protocol cost.  indices[j] receives the caller index of the j-th
+ * best sequence and *results[j] its record (same fields as opalSearchDatabase gives it at that search level);
+ * both arrays have k entries, *found (nullable) = min(k, dbLength) of them are written.
+ */
+int opalb200_db_search_topk(OpalB200Db* handle, const unsigned char query[], int queryLength,
+                            int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength,
+                            int searchType, int mode, int k, int* indices, struct OpalSearchResult* results[], int* found);
+
 /* Statistics of the last search on this handle: kernels launched, targets re-run in 32 bits, and the
  * geometry of the last launched class (threads per target pair, query rows per thread, passes over the
  * query, resident warps per SM scheduler partition), and the number of concurrent launch groups. Any pointer may be NULL. */

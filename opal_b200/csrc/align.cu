@@ -293,12 +293,14 @@ bool replay_ok(const unsigned char* q, int Q, const unsigned char* t, int T, con
 }  // namespace
 
 int align_database(DeviceDb* ddb, const unsigned char* query, int Q, unsigned char* const* db, int n, const int* lens,
-                   int Go, int Ge, const int* matrix, int A, OpalSearchResult* results[], int mode) {
+                   int Go, int Ge, const int* matrix, int A, OpalSearchResult* results[], int mode, const int* subset) {
     if (!ddb || !ddb->ensure_uploaded()) return OPAL_B200_ERR_CUDA;
     // target i on the host: the caller's pointer, or (resident-handle calls) the database's own sorted copy
-    auto target_len = [&](int i) { return lens ? lens[i] : ddb->sorted_lengths()[ddb->sorted_position()[i]]; };
-    auto target_ptr = [&](int i) -> const unsigned char* {
-        return db ? db[i] : ddb->h_residues() + ddb->offsets()[ddb->sorted_position()[i]];
+    // record j describes database entry entry(j): all of them, or the given subset (top-k pipelines)
+    auto entry = [&](int j) { return subset ? subset[j] : j; };
+    auto target_len = [&](int j) { return lens ? lens[entry(j)] : ddb->sorted_lengths()[ddb->sorted_position()[entry(j)]]; };
+    auto target_ptr = [&](int j) -> const unsigned char* {
+        return db ? db[entry(j)] : ddb->h_residues() + ddb->offsets()[ddb->sorted_position()[entry(j)]];
     };
     int M = matrix[0];
     for (int i = 1; i < A * A; i++) M = std::max(M, matrix[i]);
@@ -370,7 +372,7 @@ int align_database(DeviceDb* ddb, const unsigned char* query, int Q, unsigned ch
                     if (!tasks.empty() && flagWords + words > budgetWords) break;
                     if (round == 0 && band_borders(tk.score, mode, tk.Qp, tk.Tp, Go, Ge, M, &tk.bottom, &tk.top)) {}
                     else { tk.bottom = tk.Qp - 1; tk.top = tk.Tp - 1; }
-                    tk.targetOffset = ddb->offsets()[ddb->sorted_position()[i]];
+                    tk.targetOffset = ddb->offsets()[ddb->sorted_position()[entry(i)]];
                     tk.flagOffset = flagWords; tk.eqOffset = flagWords; tk.opsOffset = opsBytes; tk.bndOffset = bndInts;
                     flagWords += words; opsBytes += tk.Qp + tk.Tp + 8; bndInts += 2LL * tk.Tp;
                     tasks.push_back(tk); ids.push_back(i);

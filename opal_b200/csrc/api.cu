@@ -3,6 +3,7 @@
 // opalSearchDatabase mirrors reference src/opal.cpp:1435-1519 step by step -- skip mask from
 // prefilled records, score/end search, early return on error, then either the alignment stage
 // or the "no alignment" field fill -- with the SIMD passes replaced by DeviceDb::search.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -215,6 +216,41 @@ int opalb200_db_search_results(OpalB200Db* h, const unsigned char query[], int q
     DeviceDb* ddb = reinterpret_cast<DeviceDb*>(h);
     return search_into_results(ddb, query, queryLength, nullptr, ddb->size(), nullptr, gapOpen, gapExt, scoreMatrix, alphabetLength,
                                results, searchType, mode);
+}
+
+int opalb200_db_search_topk(OpalB200Db* h, const unsigned char query[], int queryLength, int gapOpen, int gapExt,
+                            const int* scoreMatrix, int alphabetLength, int searchType, int mode, int k, int* indices,
+                            OpalSearchResult* results[], int* found) {
+    if (found) *found = 0;
+    if (!h || !indices || !results || k < 0) return OPAL_ERR_NO_SIMD_SUPPORT;
+    DeviceGuard guard;
+    DeviceDb* ddb = reinterpret_cast<DeviceDb*>(h);
+    const int n = ddb->size(), kk = std::min(k, n);
+    std::vector<int> sc((size_t)n), eq((size_t)n, -1), et((size_t)n, -1);
+    const int wantEnd = searchType != OPAL_SEARCH_SCORE;
+    int status = ddb->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd, mode, nullptr, sc.data(),
+                             eq.data(), et.data(), nullptr);
+    if (status) return status;
+    // the k best: score descending, caller index ascending among equals
+    std::vector<int> idx((size_t)n);
+    for (int i = 0; i < n; i++) idx[i] = i;
+    auto better = [&](int a, int b) { return sc[a] != sc[b] ? sc[a] > sc[b] : a < b; };
+    if (kk < n) std::nth_element(idx.begin(), idx.begin() + kk, idx.end(), better);
+    std::sort(idx.begin(), idx.begin() + kk, better);
+    for (int j = 0; j < kk; j++) {
+        const int i = idx[j];
+        indices[j] = i;
+        opalInitSearchResult(results[j]);
+        opalSearchResultSetScore(results[j], sc[i]);
+        results[j]->endLocationQuery = wantEnd ? eq[i] : -1;
+        results[j]->endLocationTarget = wantEnd ? et[i] : -1;
+        results[j]->alignmentLength = -1;  // as opalSearchDatabase leaves it below OPAL_SEARCH_ALIGNMENT (:1508-1515)
+    }
+    if (found) *found = kk;
+    if (searchType == OPAL_SEARCH_ALIGNMENT && kk > 0)
+        status = align_database(ddb, query, queryLength, nullptr, kk, nullptr, gapOpen, gapExt, scoreMatrix, alphabetLength, results,
+                                mode, indices);
+    return status;
 }
 
 void opalb200_db_last_stats(const OpalB200Db* h, int* kernelLaunches, int* rerun32, int* G, int* R, int* passes,

@@ -34,6 +34,8 @@ class OpalB200(OpalCLibrary):
         L.opalb200_db_search_batch.restype = ci
         L.opalb200_db_search_results.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp, ci, ci]
         L.opalb200_db_search_results.restype = ci
+        L.opalb200_db_search_topk.argtypes = [vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, vp, vp, ctypes.POINTER(ci)]
+        L.opalb200_db_search_topk.restype = ci
         L.opalb200_db_destroy.argtypes = [vp]
         L.opalb200_db_destroy.restype = None
         L.opalb200_db_length.argtypes = [vp]
@@ -136,6 +138,22 @@ class ResidentDb:
             self.handle, qbuf.ctypes.data, int(query.size), int(gap_open), int(gap_ext), sm.ctypes.data,
             int(alphabet_length), rp.ctypes.data, int(search_type), int(mode))
         return rc, results
+
+    def search_topk(self, query, gap_open, gap_ext, score_matrix, alphabet_length, search_type, mode, k):
+        """opalb200_db_search_topk. Returns (rc, indices[found], results[found])."""
+        query = np.ascontiguousarray(query, dtype=np.uint8)
+        sm = np.ascontiguousarray(score_matrix, dtype=np.int32).ravel()
+        results = new_results(max(int(k), 1))
+        rp = result_pointers(results)
+        idx = np.full(max(int(k), 1), -1, dtype=np.int32)
+        found = ctypes.c_int(0)
+        qbuf = query if query.size else np.zeros(1, dtype=np.uint8)
+        if isinstance(mode, str):
+            mode = MODES[mode]
+        rc = self.eng.lib.opalb200_db_search_topk(
+            self.handle, qbuf.ctypes.data, int(query.size), int(gap_open), int(gap_ext), sm.ctypes.data,
+            int(alphabet_length), int(search_type), int(mode), int(k), idx.ctypes.data, rp.ctypes.data, ctypes.byref(found))
+        return rc, idx[:found.value], results[:found.value]
 
     def last_stats(self):
         v = [ctypes.c_int(0) for _ in range(7)]

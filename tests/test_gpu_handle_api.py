@@ -147,3 +147,43 @@ def test_handle_records_empty_and_invalid_mode(product):
         assert rc == 3 and res["scoreSet"][0] == 0  # OPAL_ERR_INVALID_MODE, results untouched
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("mode", ["SW", "NW", "HW", "OV"])
+def test_topk_pipeline_equals_the_two_call_protocol(product, mode):
+    """BASELINE configs[3] in one call: score -> top-k -> alignment on the resident database must give the records
+    the reference protocol gives (score+end over the database, top k by (score desc, index asc), ALIGNMENT over the
+    k-entry sub-database with the prefilled records)."""
+    rng = np.random.default_rng(9)
+    sm = matrices.blosum62()
+    q = datasets.random_residues(110, rng, sm)
+    db = _random_db(rng, sm, 300, 1, 330, planted=q)
+    k = 37
+    rc, res = product.search_database(q, db, 11, 1, sm.flat(), 23, None, 1, MODES[mode])
+    assert rc == 0
+    order = sorted(range(len(db)), key=lambda i: (-int(res["score"][i]), i))[:k]
+    pre = res[order].copy()
+    rc, res2 = product.search_database(q, db.subset(order), 11, 1, sm.flat(), 23, pre, 2, MODES[mode])
+    assert rc == 0
+    want = dump_results(res2)
+    free_alignments(res2)
+    h = product.create_db(db, 0)
+    try:
+        rc, idx, top = h.search_topk(q, 11, 1, sm.flat(), 23, 2, mode, k)
+        assert rc == 0, product.last_error()
+        assert idx.tolist() == order
+        got = dump_results(top)
+        free_alignments(top)
+        assert got == want, [(i, g, w) for i, (g, w) in enumerate(zip(got, want)) if g != w][:3]
+        # lower search levels: the same records as opalSearchDatabase gives the selected entries
+        for st in (0, 1):
+            rc, idx, top = h.search_topk(q, 11, 1, sm.flat(), 23, st, mode, k)
+            rc2, full = product.search_database(q, db, 11, 1, sm.flat(), 23, None, st, MODES[mode])
+            assert rc == 0 and rc2 == 0 and idx.tolist() == order
+            assert dump_results(top) == [dump_results(full)[i] for i in order]
+        rc, idx, top = h.search_topk(q, 11, 1, sm.flat(), 23, 1, mode, 10 ** 6)  # k beyond the database
+        assert rc == 0 and len(idx) == len(db) and sorted(idx.tolist()) == list(range(len(db)))
+        rc, idx, top = h.search_topk(q, 11, 1, sm.flat(), 23, 1, mode, 0)
+        assert rc == 0 and len(idx) == 0
+    finally:
+        h.close()

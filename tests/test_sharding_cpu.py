@@ -77,7 +77,8 @@ def test_c_abi_exports_every_declared_symbol():
         declared |= set(re.findall(r"\b(opal[A-Za-z0-9_]+)\s*\(", text))
     assert {"opalSearchDatabase", "opalSearchDatabaseCharSW", "opalSearchDatabaseRescore", "opalInitSearchResult",
             "opalSearchResultIsEmpty", "opalSearchResultSetScore", "opalb200_db_create", "opalb200_db_search",
-            "opalb200_db_create_sorted", "opalb200_db_search_batch", "opalb200_db_search_results"} <= declared
+            "opalb200_db_create_sorted", "opalb200_db_search_batch", "opalb200_db_search_results",
+            "opalb200_db_search_topk"} <= declared
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared in include/ but not exported"
 

@@ -37,4 +37,14 @@ for scale, go, ge in ((1, 11, 1), (8, 88, 8)):
         same = same and all((get_alignment(out, i) == get_alignment(want, i)).all() for i in range(len(sub)))
         print(f"     reference (1 thread) {1e3*(t5-t4):.1f} ms, identical records + operation strings: {same}")
         free_alignments(want)
+    # the same protocol as ONE call on the resident database (opalb200_db_search_topk)
+    h = eng.create_db(db, 0)
+    for rep in range(3):
+        t6 = time.perf_counter()
+        rck, idx, topres = h.search_topk(q, go, ge, m, 23, 2, "SW", 1000)
+        t7 = time.perf_counter()
+        same_k = (idx == top).all() and all((topres[f] == out[f]).all() for f in ("score", "endLocationQuery", "endLocationTarget", "startLocationQuery", "startLocationTarget", "alignmentLength"))
+        free_alignments(topres)
+    print(f"     resident top-k pipeline (score+end over {len(db)} + top-1000 alignment): {1e3*(t7-t6):.2f} ms (rc {rck}), same records as the two-call protocol: {bool(same_k)}")
+    h.close()
     free_alignments(out)
