@@ -138,3 +138,23 @@ def test_top_hits_alignment_with_32_bit_rescoring_config4_in_miniature(product, 
     rc2, got = search_dump(product, q, sub, 88, 8, m8, 23, 2, MODES["SW"], results=pre_p, entry="opalSearchDatabaseRescore")
     assert rc1 == rc2 == 0
     assert got == want
+
+
+@pytest.mark.parametrize("mode,go,ge", [("SW", 10, 2), ("NW", 10, 2), ("HW", 10, 2), ("OV", 10, 2), ("SW", 16, 4)])
+def test_config5_miniature_long_dna_query_many_passes(product, oracle, mode, go, ge):
+    """BASELINE configs[4] in miniature: DNA alphabet, a query far longer than one strip of rows (many passes over
+    the query with boundary rows in HBM), heavy-tailed target lengths, and planted near-copies of the query whose
+    score leaves 16 bits (32-bit re-run for SW, a-priori 32-bit routing for the global modes).  With gaps 10/2 random
+    DNA scores grow linearly with length (every SW end location needs the exact re-sweep); 16/4 is the logarithmic
+    regime tools/config5_probe.py measures."""
+    rng = np.random.default_rng(55)
+    sm = matrices.simple(4, 5, -4)
+    q = rng.integers(0, 4, 7200, dtype=np.uint8)
+    db = datasets.dna_db(48, 55, query=q, xmin=60, max_len=9000, n_at_max=2, n_planted=3)
+    for st in (0, 1):
+        rc1, want = search_dump(oracle, q, db, go, ge, sm.flat(), 4, st, MODES[mode])
+        rc2, got = search_dump(product, q, db, go, ge, sm.flat(), 4, st, MODES[mode])
+        assert rc1 == rc2 == 0
+        assert got == want, [(i, g, w) for i, (g, w) in enumerate(zip(got, want)) if g != w][:3]
+    if mode == "SW":
+        assert max(w[1] for w in want) > 32767  # the planted copies really leave the 16-bit range
