@@ -7,6 +7,8 @@
 // global counter, and the 16 -> 32 bit escalation re-runs exactly the flagged targets.
 #include "engine.h"
 
+#include <emmintrin.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -199,6 +201,27 @@ static bool device_info(int device, DeviceInfo* out) {
     return true;
 }
 
+// Copy with non-temporal stores: the staged bytes go to memory instead of staying dirty in the writing core's
+// cache, where the copy engine would have to fetch them line by line through the coherence fabric.
+static void stream_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+    if (n < 256) { memcpy(dst, src, n); return; }
+    const size_t head = (16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15;
+    memcpy(dst, src, head);
+    dst += head; src += head; n -= head;
+    size_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 16));
+        const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 32));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 48));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 16), b);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 32), c);
+        _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 48), d);
+    }
+    memcpy(dst + i, src + i, n - i);
+}
+
 // ------------------------------------------------------------------ host worker pool
 // Packing a database is a host-side gather of every sequence into pinned memory; on the drop-in path it is paid
 // per call and is memory-bound on one core, so it is spread over a few persistent threads (the reference arm of
@@ -379,28 +402,42 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
 }
 
 // One thread per entry of the paired stream (pads included), so that a 35 000-residue target costs what 35 000
-// residues cost and not one warp's walk along it.  The pair an entry belongs to is found by bisection.
+// residues cost and not one warp's walk along it.  The first thread of a block finds the pair of the block's first
+// entry by bisection; the other threads walk forward from there (a pair spans at least 33 entries, so a block of
+// 256 touches at most 8 of them).
 static __global__ void pack_pairs_kernel(const uint8_t* residues, const long long* offsets, const int* lengths, int numTargets,
                                   const long long* pairOffsets, int numPairs, long long entries, uint16_t* pairStream, int* maxCode) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t word = 0;
-    if (e < entries) {
-        int lo = 0, hi = numPairs;  // last pair whose first column is at or before e (entries before pair 0 are padding)
+    __shared__ int basePair, blockMax;
+    const long long e0 = (long long)blockIdx.x * blockDim.x;
+    if (threadIdx.x == 0) {
+        blockMax = 0;
+        int lo = 0, hi = numPairs;  // last pair whose first column is at or before e0 (entries before pair 0 are padding)
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if (pairOffsets[mid] <= e) lo = mid; else hi = mid;
+            if (pairOffsets[mid] <= e0) lo = mid; else hi = mid;
         }
-        const long long c = e - pairOffsets[lo];
-        const int a = 2 * lo, b = 2 * lo + 1;
-        if (numPairs > 0 && c >= 0 && c < lengths[a]) {
+        basePair = lo;
+    }
+    __syncthreads();
+    const long long e = e0 + threadIdx.x;
+    uint32_t word = 0;
+    if (e < entries && numPairs > 0) {
+        int p = basePair;
+        while (p + 1 < numPairs && pairOffsets[p + 1] <= e) p++;
+        const long long c = e - pairOffsets[p];
+        const int a = 2 * p, b = 2 * p + 1;
+        if (c >= 0 && c < lengths[a]) {
             word = (uint32_t)residues[offsets[a] + c] + 1u;
             if (b < numTargets && c < lengths[b]) word |= ((uint32_t)residues[offsets[b] + c] + 1u) << 8;
         }
-        pairStream[e] = (uint16_t)word;
     }
+    if (e < entries) pairStream[e] = (uint16_t)word;
     uint32_t mx = max(word & 0xffu, word >> 8);
     mx = __reduce_max_sync(0xffffffffu, mx);
-    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(maxCode, (int)mx - 1);  // largest residue code seen
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&blockMax, (int)mx);
+    __syncthreads();
+    // largest residue code seen: one global atomic per block, and only while it still raises the value
+    if (threadIdx.x == 0 && blockMax > 0 && blockMax - 1 > *(volatile int*)maxCode) atomicMax(maxCode, blockMax - 1);
 }
 
 // ------------------------------------------------------------------ DeviceDb
@@ -528,14 +565,18 @@ DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed,
         uint8_t* staging = d->hResidues_;
         memset(staging + total, 0, 64);
         // Parts of about equal residue count, cut at sequence boundaries; each is uploaded as soon as it and all
-        // parts before it are staged, so the copy engine runs behind the host copy.  Small databases are staged by
-        // the calling thread alone: the DMA engine reads lines that sit dirty in ONE core's cache at full speed,
-        // and several times slower when they are spread over the caches of many cores (measured: 4.5 MB in 96 us
-        // after a 1-thread copy, 680 us after a 16-thread one).  Large databases do not fit in any cache and
-        // take the host pool.
+        // parts before it are staged, so the copy engine runs behind the host copy.  The copy engine reads lines
+        // that sit dirty in ONE core's cache at full speed and several times slower when they are spread over the
+        // caches of many cores (measured: 4.5 MB in 96 us after a 1-thread memcpy, 680 us after a 16-thread one).
+        // So: long runs are copied with non-temporal stores (nothing stays in a cache) and may be split over a
+        // few threads; scattered short sequences are copied by the calling thread alone unless the database is
+        // far larger than the caches.
         HostPool& pool = HostPool::get();
-        const bool threaded = total >= (64LL << 20) && pool.width() > 1;
-        const long long partBytes = threaded ? (8 << 20) : (1 << 20);
+        const bool oneRun = packed || (n > 0 && db[n - 1] + lens[n - 1] == db[0] + total);  // the usual arena-loaded database
+        int stageThreads = total >= (64LL << 20) ? pool.width() : (oneRun && total >= (2 << 20) ? std::min(pool.width(), 8) : 1);
+        if (const char* e = getenv("OPAL_B200_STAGE_THREADS")) stageThreads = std::max(1, std::min(atoi(e), pool.width()));
+        const bool threaded = stageThreads > 1;
+        const long long partBytes = total >= (64LL << 20) ? (8 << 20) : std::max<long long>(256 << 10, total / stageThreads);
         const int parts = (int)std::max<long long>(1, std::min<long long>(total / partBytes, 4096));
         std::vector<int> cut((size_t)parts + 1, n);
         cut[0] = 0;
@@ -546,15 +587,17 @@ DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed,
         auto stage = [&](int k) {
             const int lo = cut[k], hi = cut[k + 1];
             if (lo >= hi) return;
-            if (packed) { memcpy(staging + copyOff[lo], packed + copyOff[lo], (size_t)(copyOff[hi] - copyOff[lo])); return; }
+            if (packed) { stream_copy(staging + copyOff[lo], packed + copyOff[lo], (size_t)(copyOff[hi] - copyOff[lo])); _mm_sfence(); return; }
             int j = lo;
-            while (j < hi) {  // one memcpy per run of sequences that are adjacent in the caller's memory
+            while (j < hi) {  // one copy per run of sequences that are adjacent in the caller's memory
                 int e = j + 1;
                 while (e < hi && db[e] == db[e - 1] + lens[e - 1]) e++;
                 const long long len = copyOff[e] - copyOff[j];
-                if (len > 0) memcpy(staging + copyOff[j], db[j], (size_t)len);
+                if (len >= 4096) stream_copy(staging + copyOff[j], db[j], (size_t)len);
+                else if (len > 0) memcpy(staging + copyOff[j], db[j], (size_t)len);
                 j = e;
             }
+            _mm_sfence();
         };
         cudaError_t copyError = cudaSuccess;
         size_t uploaded = 0;  // bytes of the block already handed to the copy engine
