@@ -345,6 +345,15 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
             if (!firstPass && t == 0 && Tmax > 0) { nextBH = bH[0]; nextBF = bF[0]; }
         };
 
+        // OV: best cell of the last target column among this thread's rows (first row on ties), half-word l
+        auto scan_last_column = [&](int l) {
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const int r = myRow0 + j;
+                const int v = TR::lane(HG[j], l) + Go;
+                if (r >= 0 && r < p.Q && v > lcScore[l]) { lcScore[l] = v; lcRow[l] = r; }
+            }
+        };
         // residues of column cc as (y0 + 1) | (y1 + 1) << 8, 0 = none.  The paired stream is padded, so
         // only the upper clamp is needed (a group may idle while longer groups of its warp finish).
         auto fetch = [&](int cc) -> uint32_t {
@@ -478,19 +487,12 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
                             if (!pl) colLo = c;
                             if (LANES == 2 && !ph) colHi = c;
                         }
-                        // last target column (OV): every real row of this thread
-                        if (mode == kModeOV) {
-    #pragma unroll
-                            for (int l = 0; l < LANES; l++)
-                                if (c == T[l] - 1) {
-    #pragma unroll
-                                    for (int j = 0; j < R; j++) {
-                                        const int r = myRow0 + j;
-                                        const int v = TR::lane(HG[j], l) + Go;
-                                        if (r >= 0 && r < p.Q && v > lcScore[l]) { lcScore[l] = v; lcRow[l] = r; }
-                                    }
-                                }
-                        }
+                        // last target column (OV): every real row of this thread.  Only the shorter member of a
+                        // pair of unequal lengths is scanned here, where each thread meets that column at a step
+                        // of its own (one active thread per scan); the longer member -- and the shorter one when
+                        // the lengths are equal, the usual case in a large sorted database -- is still sitting in
+                        // HG[] when the sweep ends and is scanned there by all threads at once.
+                        if (mode == kModeOV && LANES == 2 && T[1] != T[0] && c == T[1] - 1) scan_last_column(1);
                     }
                 }
                 if (!lastPass) {  // kernel-uniform: single-pass searches skip the boundary row entirely
@@ -549,6 +551,11 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
         } else {
             init_state(false);
             sweep(std::integral_constant<int, FLAVOR>());
+            if (FLAVOR == kFlavorGlobal && mode == kModeOV) {
+                // threads stop updating their rows after the last column of the longer member: it is still in HG[]
+                if (T[0] > 0) scan_last_column(0);
+                if (LANES == 2 && T[1] == T[0] && T[1] > 0) scan_last_column(1);
+            }
             reduce(false);
         }
         const bool pairInexact = false;
