@@ -478,12 +478,14 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
                                 }
                         }
                     } else {
-                        // last query row (HW, OV): register R-1 of thread G-1 in the last pass
-                        if (lastPass && t == G - 1) {
-                            reg cand = u;
-                            if (LANES == 2) cand = TR::pack(c < T[0] ? TR::lane(u, 0) : TR::NEG, c < T[1] ? TR::lane(u, 1) : TR::NEG);
+                        // last query row (HW, OV): register R-1 of thread G-1 in the last pass.  Every thread runs the
+                        // three instructions (only thread G-1's result is read), which is cheaper than branching
+                        // around them.  The shorter member of a pair needs no mask in the columns past its end: a
+                        // cell there is reached through a horizontal gap from its last real column, so it is
+                        // strictly below the value that column already contributed.
+                        if (lastPass) {
                             bool ph, pl;
-                            best = TR::bmax(best, cand, &ph, &pl);
+                            best = TR::bmax(best, u, &ph, &pl);
                             if (!pl) colLo = c;
                             if (LANES == 2 && !ph) colHi = c;
                         }
