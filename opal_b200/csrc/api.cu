@@ -4,6 +4,7 @@
 // prefilled records, score/end search, early return on error, then either the alignment stage
 // or the "no alignment" field fill -- with the SIMD passes replaced by DeviceDb::search.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -56,13 +57,20 @@ static int search_into_results(DeviceDb* ddb, const unsigned char* query, int qu
     if (dbLength <= 0) return 0;
 
     // Entries that already hold what this search level needs are not recomputed (:1446-1451).
+    // (The loops over all records run on the host pool for large databases: half a million 40-byte records cost
+    // milliseconds per pass on one core.)
     std::vector<unsigned char> skip(dbLength);
-    bool anyWork = false;
-    for (int i = 0; i < dbLength; i++) {
-        const OpalSearchResult* r = results[i];
-        skip[i] = r->scoreSet && (searchType == OPAL_SEARCH_SCORE || (r->endLocationQuery >= 0 && r->endLocationTarget >= 0));
-        anyWork |= !skip[i];
-    }
+    std::atomic<bool> anyWorkFlag(false);
+    parallel_for(dbLength, 65536, [&](long long lo, long long hi) {
+        bool any = false;
+        for (long long i = lo; i < hi; i++) {
+            const OpalSearchResult* r = results[i];
+            skip[i] = r->scoreSet && (searchType == OPAL_SEARCH_SCORE || (r->endLocationQuery >= 0 && r->endLocationTarget >= 0));
+            any |= !skip[i];
+        }
+        if (any) anyWorkFlag.store(true);
+    });
+    const bool anyWork = anyWorkFlag.load();
     const int wantEnd = searchType != OPAL_SEARCH_SCORE;
     const bool trace = getenv("OPAL_B200_TRACE") != nullptr;  // phase timings of the call on stderr
     auto now = [] { return std::chrono::steady_clock::now(); };
@@ -82,12 +90,19 @@ static int search_into_results(DeviceDb* ddb, const unsigned char* query, int qu
         status = ddb->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd, mode, skip.data(),
                              sc.data(), eq.data(), et.data(), nullptr);
         if (status == 0) {
-            for (int i = 0; i < dbLength; i++) {
-                if (skip[i]) continue;
-                opalSearchResultSetScore(results[i], sc[i]);
-                results[i]->endLocationQuery = wantEnd ? eq[i] : -1;  // :420-426, 869-905
-                results[i]->endLocationTarget = wantEnd ? et[i] : -1;
-            }
+            parallel_for(dbLength, 65536, [&](long long lo, long long hi) {
+                for (long long i = lo; i < hi; i++) {
+                    if (skip[i]) continue;
+                    opalSearchResultSetScore(results[i], sc[i]);
+                    results[i]->endLocationQuery = wantEnd ? eq[i] : -1;  // :420-426, 869-905
+                    results[i]->endLocationTarget = wantEnd ? et[i] : -1;
+                    if (searchType != OPAL_SEARCH_ALIGNMENT) {  // :1508-1515, same pass
+                        results[i]->alignment = NULL;
+                        results[i]->alignmentLength = -1;
+                        results[i]->startLocationQuery = results[i]->startLocationTarget = -1;
+                    }
+                }
+            });
         }
     }
     const auto t2 = now();
@@ -100,13 +115,16 @@ static int search_into_results(DeviceDb* ddb, const unsigned char* query, int qu
         fprintf(stderr, "[opal-b200] pack+upload %.3f ms, search %.3f ms, alignment %.3f ms, release %.3f ms\n", ms(t0, t1), ms(t1, t2),
                 ms(t2, t3), ms(t3, now()));
     if (status) return status;  // :1473
-    if (searchType != OPAL_SEARCH_ALIGNMENT) {  // :1508-1515
-        for (int i = 0; i < dbLength; i++) {
-            results[i]->alignment = NULL;
-            results[i]->alignmentLength = -1;
-            results[i]->startLocationQuery = -1;
-            results[i]->startLocationTarget = -1;
-        }
+    if (searchType != OPAL_SEARCH_ALIGNMENT) {  // :1508-1515: every entry, skipped ones included (the others were done above)
+        parallel_for(dbLength, 65536, [&](long long lo, long long hi) {
+            for (long long i = lo; i < hi; i++) {
+                if (anyWork && !skip[i]) continue;
+                results[i]->alignment = NULL;
+                results[i]->alignmentLength = -1;
+                results[i]->startLocationQuery = -1;
+                results[i]->startLocationTarget = -1;
+            }
+        });
     }
     return 0;
 }

@@ -309,6 +309,32 @@ private:
 };
 }  // namespace
 
+void parallel_for(long long n, long long grain, const std::function<void(long long, long long)>& body) {
+    HostPool& pool = HostPool::get();
+    const int parts = (int)std::max<long long>(1, std::min<long long>(n / std::max<long long>(grain, 1), pool.width()));
+    if (parts <= 1) { body(0, n); return; }
+    pool.run(parts, [&](int k) { body(n * k / parts, n * (k + 1) / parts); }, [](int) {});
+}
+
+// The index vectors of a database (a few MB for half a million sequences) are recycled between databases: a
+// drop-in call builds and drops one per call, and fresh heap memory of that size is page-faulted in every time.
+namespace {
+struct HostArrays { std::vector<int> order, pos, sortedLen; std::vector<long long> offsets, copyOff; };
+std::mutex g_arraysMu;
+std::vector<HostArrays> g_arrays;
+HostArrays take_host_arrays() {
+    std::lock_guard<std::mutex> lk(g_arraysMu);
+    if (g_arrays.empty()) return HostArrays();
+    HostArrays h = std::move(g_arrays.back());
+    g_arrays.pop_back();
+    return h;
+}
+void give_host_arrays(HostArrays&& h) {
+    std::lock_guard<std::mutex> lk(g_arraysMu);
+    if (g_arrays.size() < 4 && h.order.capacity() <= (64u << 20)) g_arrays.push_back(std::move(h));
+}
+}  // namespace
+
 // Thread stride in the profile: a multiple of 4 words (16-byte aligned LDS.128) with an odd number of
 // 16-byte units, so the 8 lanes of a quarter-warp hit 8 different bank groups whatever their residues are.
 static int rpad_of(int R) { const int r4 = (R + 3) / 4; return 4 * ((r4 % 2 == 0) ? r4 + 1 : r4); }
@@ -500,10 +526,31 @@ DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed,
             if (lens[i] < 0) { set_error("negative sequence length"); return false; }
             maxLen = std::max(maxLen, lens[i]);
         }
+        {
+            HostArrays h = take_host_arrays();
+            d->order_.swap(h.order); d->pos_.swap(h.pos); d->sortedLen_.swap(h.sortedLen); d->offsets_.swap(h.offsets);
+            d->copyOff_.swap(h.copyOff);
+        }
         d->order_.resize(n);
         d->pos_.resize(n);
         if (packed) {
             for (int p = 0; p < n; p++) d->order_[p] = order ? order[p] : p;
+        } else if (maxLen <= (1 << 22) && n >= (1 << 17) && (long long)HostPool::get().width() * (maxLen + 2) <= (16LL << 20)) {
+            // large database: the same counting sort with one histogram per host thread (contiguous index ranges,
+            // so the result is still stable in caller order) -- the scatter is a cache miss per sequence
+            const int W = HostPool::get().width(), B = maxLen + 1;
+            std::vector<int> hist((size_t)W * B, 0);
+            HostPool::get().run(W, [&](int k) {
+                int* h = hist.data() + (size_t)k * B;
+                for (long long i = (long long)n * k / W, e = (long long)n * (k + 1) / W; i < e; i++) h[maxLen - lens[i]]++;
+            }, [](int) {});
+            int at = 0;
+            for (int b = 0; b < B; b++)
+                for (int k = 0; k < W; k++) { const int c = hist[(size_t)k * B + b]; hist[(size_t)k * B + b] = at; at += c; }
+            HostPool::get().run(W, [&](int k) {
+                int* h = hist.data() + (size_t)k * B;
+                for (long long i = (long long)n * k / W, e = (long long)n * (k + 1) / W; i < e; i++) d->order_[h[maxLen - lens[i]]++] = (int)i;
+            }, [](int) {});
         } else if (maxLen <= (1 << 22)) {
             std::vector<int> start(maxLen + 2, 0);
             for (int i = 0; i < n; i++) start[maxLen - lens[i] + 1]++;
@@ -517,18 +564,21 @@ DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed,
         // reads of the caller's memory, runs of adjacent sequences merge into one memcpy), sorted order for a
         // packed database -- and offsets_[p] says where sorted position p lives.  Nothing needs the sorted
         // sequences to be adjacent: the 16-bit kernels stream the paired layout built on the device below.
-        std::vector<long long> copyOff((size_t)n + 1);  // in copy order
+        std::vector<long long>& copyOff = d->copyOff_;  // offsets in copy order (scratch of this function, recycled)
+        copyOff.resize((size_t)n + 1);
         long long total = 0;
         for (int i = 0; i < n; i++) { copyOff[i] = total; total += lens[i]; }
         copyOff[n] = total;
         d->sortedLen_.resize(n);
         d->offsets_.resize((size_t)n + 1);
-        for (int p = 0; p < n; p++) {
-            const int i = d->order_[p];
-            d->pos_[i] = p;
-            d->sortedLen_[p] = packed ? lens[p] : lens[i];
-            d->offsets_[p] = packed ? copyOff[p] : copyOff[i];
-        }
+        parallel_for(n, 65536, [&](long long lo, long long hi) {
+            for (long long p = lo; p < hi; p++) {
+                const int i = d->order_[p];
+                d->pos_[i] = (int)p;
+                d->sortedLen_[p] = packed ? lens[p] : lens[i];
+                d->offsets_[p] = packed ? copyOff[p] : copyOff[i];
+            }
+        });
         d->offsets_[n] = total;
         d->totalResidues_ = total;
         trace.mark("sort");
@@ -652,6 +702,10 @@ DeviceDb* DeviceDb::clone_context() {
     DeviceDb* c = new DeviceDb();
     c->ownsDb_ = false; c->uploaded_ = true;
     c->device_ = device_; c->n_ = n_; c->numSMs_ = numSMs_; c->smemLimit_ = smemLimit_; c->totalResidues_ = totalResidues_;
+    {
+        HostArrays h = take_host_arrays();
+        c->order_.swap(h.order); c->pos_.swap(h.pos); c->sortedLen_.swap(h.sortedLen); c->offsets_.swap(h.offsets);
+    }
     c->order_ = order_; c->pos_ = pos_; c->sortedLen_ = sortedLen_; c->offsets_ = offsets_;
     c->hResidues_ = hResidues_; c->dResidues_ = dResidues_; c->dOffsets_ = dOffsets_; c->dLengths_ = dLengths_;
     c->dPairStream_ = dPairStream_; c->dPairOffsets_ = dPairOffsets_; c->numPairs_ = numPairs_; c->maxCode_ = maxCode_;
@@ -660,6 +714,11 @@ DeviceDb* DeviceDb::clone_context() {
 }
 
 DeviceDb::~DeviceDb() {
+    {
+        HostArrays h;
+        h.order.swap(order_); h.pos.swap(pos_); h.sortedLen.swap(sortedLen_); h.offsets.swap(offsets_); h.copyOff.swap(copyOff_);
+        give_host_arrays(std::move(h));
+    }
     cudaSetDevice(device_);
     for (DeviceDb* c : contexts_) delete c;
     if (stream_) cudaStreamSynchronize(stream_);
@@ -996,15 +1055,26 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
             trace.mark("wait");
             return true;
         };
+        // results go back to caller order: a scatter, split over the host pool for large databases
         auto publish = [&](const std::vector<int>& list, std::vector<int>* overflowed) {
-            for (int p : list) {
-                const int i = order_[p];
-                const int sc = hScore_[p];
-                if (sc == kScoreOverflow || sc == kScoreNone) { if (overflowed) overflowed->push_back(p); else rc = OPAL_B200_ERR_OVERFLOW; continue; }
-                scores[i] = sc;
-                if (endQ) endQ[i] = (wantEnd && hEndQ_[p] != 0x7fffffff) ? hEndQ_[p] : -1;
-                if (endT) endT[i] = (wantEnd && hEndT_[p] != 0x7fffffff) ? hEndT_[p] : -1;
-            }
+            std::mutex mu;
+            parallel_for((long long)list.size(), 65536, [&](long long lo, long long hi) {
+                std::vector<int> flagged;
+                for (long long k = lo; k < hi; k++) {
+                    const int p = list[(size_t)k], i = order_[p];
+                    const int sc = hScore_[p];
+                    if (sc == kScoreOverflow || sc == kScoreNone) { flagged.push_back(p); continue; }
+                    scores[i] = sc;
+                    if (endQ) endQ[i] = (wantEnd && hEndQ_[p] != 0x7fffffff) ? hEndQ_[p] : -1;
+                    if (endT) endT[i] = (wantEnd && hEndT_[p] != 0x7fffffff) ? hEndT_[p] : -1;
+                }
+                if (!flagged.empty()) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (overflowed) overflowed->insert(overflowed->end(), flagged.begin(), flagged.end());
+                    else rc = OPAL_B200_ERR_OVERFLOW;
+                }
+            });
+            if (overflowed) std::sort(overflowed->begin(), overflowed->end());
         };
         // NW/HW/OV classes are independent (routed a priori) and run concurrently; SW's 32-bit class is the
         // re-run of what overflowed 16 bits and has to follow it.

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
 #include <string>
 #include <utility>
 #include <vector>
@@ -32,6 +33,9 @@ struct SearchStats {
 // Device memory from the per-device block cache (engine.cu): recycled, not returned to the driver.
 bool device_alloc(int device, void** p, size_t bytes);
 void device_release(int device, void* p);
+
+// body(lo, hi) over [0, n) in parts of at least `grain`, on the persistent host pool (the caller takes part).
+void parallel_for(long long n, long long grain, const std::function<void(long long, long long)>& body);
 
 void set_error(const std::string& msg);
 const char* last_error();
@@ -88,7 +92,7 @@ private:
     int device_ = 0, n_ = 0, numSMs_ = 0, smemLimit_ = 0;
     long long totalResidues_ = 0;
     std::vector<int> order_, pos_, sortedLen_;
-    std::vector<long long> offsets_;
+    std::vector<long long> offsets_, copyOff_;
     bool ownsDb_ = true, uploaded_ = false;  // search contexts made by clone_context() borrow the database arrays
     std::vector<DeviceDb*> contexts_;
     uint8_t* hResidues_ = nullptr;
