@@ -104,6 +104,26 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
+def ncu_dram_bytes_per_launch():
+    """DRAM bytes of the dominant kernel launch from the committed ncu capture (None if it is not there)."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_search_kernel.txt")
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    best = None
+    try:
+        cur = {}
+        for line in open(path):
+            tok = line.split()
+            if len(tok) >= 3 and tok[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and tok[1] in unit:
+                cur[tok[0]] = float(tok[2].replace(",", "")) * unit[tok[1]]
+                if len(cur) == 2:
+                    total = sum(cur.values())
+                    best = total if best is None else max(best, total)
+                    cur = {}
+        return best
+    except OSError:
+        return None
+
+
 def cpu_library():
     ref = os.path.join(ROOT, "oracle", "_ref", "libopal_ref.so")
     if os.path.exists(ref):
@@ -292,9 +312,12 @@ def run_b200_arm(args, rank, local_rank, world):
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback"
     hbm_gbs = db.total_residues * args.steps / (dev_ms / 1e3) / 1e9
+    traffic = ncu_dram_bytes_per_launch() if args.workload == "config2" else None
     roofline = {
         "bound": "dpx (integer pipe)", "achieved": per_gpu, "peak": peak_gcups, "unit": "GCUPS", "frac": per_gpu / peak_gcups,
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the dominant (bulk) search_kernel launch, from the committed "
+                        "ncu --set full capture profiles/r1_ncu_search_kernel.txt; algorithmic bytes per launch = residues of its targets",
         "peak_source": f"measured live: {instr_per_s / 1e12:.2f} T packed s16x2 thread-instr/s x 2 cells / 6 instr (SW)",
         "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                 "peak_source": hbm_src, "note": "algorithmic bytes = 1 B per DB residue per query (1/Q B per cell)"},
