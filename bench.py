@@ -41,9 +41,11 @@ def make_workload(name, rank, world):
     sm = matrices.blosum62()
     query = sm.encode(datasets.P18080)
     if name == "config2":
-        db = datasets.config2_db(sm, query, seed=20261017 + rank)
+        # weak scaling: every GPU gets a shard of exactly the same work -- the same lengths and planted homologs, the
+        # background residues redrawn per rank -- so that the per-GPU tail (the longest target) does not vary by rank
+        db = datasets.config2_db(sm, query, residue_seed=None if rank == 0 else 20261017 + rank)
         desc = ("BASELINE configs[1]: SW score+end, P18080 (Q=513) vs synthetic 12,071-seq Swiss-Prot-shaped DB, "
-                "BLOSUM62 11/1; one such shard per GPU")
+                "BLOSUM62 11/1; one such shard per GPU (same lengths, residues redrawn per rank)")
         scaling = "weak"
     elif name == "config3":
         full = datasets.config3_db(sm, query=query)
@@ -197,6 +199,8 @@ def run_b200_arm(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device; opal-b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     os.environ["OPAL_B200_DEVICE"] = str(local_rank)  # device of the drop-in entry points (they take no device argument)
+    # one process per GPU on one host: the library's host pool (packing, result scatter) gets this rank's share of the cores
+    os.environ.setdefault("OPAL_B200_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(world, 1))))
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:

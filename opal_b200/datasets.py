@@ -95,12 +95,13 @@ def _assemble(lengths, rng, sm, planted=None):
 
 
 def protein_db(n, seed, sm: ScoreMatrix, query=None, homolog_fraction=0.01, tail_fraction=0.0,
-               exact_max=False):
+               exact_max=False, residue_seed=None):
     """Swiss-Prot-shaped synthetic protein database.
 
     n sequences with log-normal lengths; `homolog_fraction` of them are mutated copies of
     `query` (30-90 % identity, with indels); `tail_fraction` of them are redrawn log-uniform in
-    [5000, 35213]; with `exact_max` one sequence has exactly 35213 residues.
+    [5000, 35213]; with `exact_max` one sequence has exactly 35213 residues.  `residue_seed` redraws the
+    background residues only: same lengths and homologs, different sequences (equal-work shards for weak scaling).
     """
     rng = np.random.default_rng(seed)
     lengths = lognormal_lengths(n, rng)
@@ -119,12 +120,12 @@ def protein_db(n, seed, sm: ScoreMatrix, query=None, homolog_fraction=0.01, tail
             left = random_residues(int(rng.integers(0, 60)), rng, sm)
             right = random_residues(int(rng.integers(0, 60)), rng, sm)
             planted[int(i)] = np.concatenate([left, core, right]).astype(np.uint8)
-    return _assemble(lengths, rng, sm, planted)
+    return _assemble(lengths, rng if residue_seed is None else np.random.default_rng(residue_seed), sm, planted)
 
 
-def config2_db(sm: ScoreMatrix, query, n=12071, seed=20261017):
+def config2_db(sm: ScoreMatrix, query, n=12071, seed=20261017, residue_seed=None):
     """BASELINE.json configs[1]: 12,071-sequence Swiss-Prot-length-distributed DB (~4.3 M residues)."""
-    return protein_db(n, seed, sm, query=query, homolog_fraction=0.01)
+    return protein_db(n, seed, sm, query=query, homolog_fraction=0.01, residue_seed=residue_seed)
 
 
 def config3_db(sm: ScoreMatrix, n=570000, seed=20261018, query=None):
