@@ -398,7 +398,14 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
         const double kEff = std::max(1.0, std::min((double)k, std::ceil(warpTasks / (numSMs * 4.0))));
         const double stepTime = kEff < 1.5 ? 17.75 * R + 104.0 : kEff * (12.8 * R + 57.0);
         const double warpsBusy = std::min((double)numSMs * 4 * k, warpTasks);
-        const double throughput = warpSteps * stepTime / warpsBusy;
+        double throughput = warpSteps * stepTime / warpsBusy;
+        // Two warps share a partition only while both have work: with few tasks per warp a large part of the run is
+        // spent with single warps finishing alone at the (slower) one-warp rate.  Measured on 10k-sequence databases:
+        // +40 % at 2.2 tasks per warp, nothing from about 3.5 tasks per warp on.
+        if (k >= 2) {
+            const double tasksPerWarp = warpTasks / ((double)numSMs * 4 * k);
+            if (tasksPerWarp < 3.5) throughput *= 1.0 + 0.3 * (3.5 - std::max(tasksPerWarp, 1.0));
+        }
         const double tail = (maxLen + G - 1) * stepTime;
         // every further pass is a kernel of its own (drain, launch, boundary rows through HBM): measured ~4 % each
         const double cost = passes * (std::max(throughput, tail) + 0.15 * std::min(throughput, tail) + 30000.0) *
