@@ -44,7 +44,8 @@ constexpr int kBlockThreads = 256;  // at most 2 warps per scheduler partition: 
 constexpr int launch_bound_for(int flavor) { return flavor == 2 ? 256 : 384; }
 constexpr int kModeNW = 0, kModeHW = 1, kModeOV = 2, kModeSW = 3;
 constexpr int kFlavorSWScore = 0, kFlavorSWEnd = 1, kFlavorGlobal = 2, kFlavorSWEndFast = 3;
-constexpr int kRowBits = 6;  // kFlavorSWEndFast: low bits of the tracked key hold 63 - row
+constexpr int kRowBits = 6;  // kFlavorSWEndFast: low bits of the tracked key hold 63 - row (latch_key_s16x2 spells the mask out)
+static_assert(kRowBits == 6, "latch_key_s16x2 saturates the row bits with 0x003f003f");
 constexpr int kScoreNone = INT32_MIN;          // "no candidate yet" in the running-result arrays
 constexpr int kScoreOverflow = INT32_MIN + 1;  // 16-bit pass: re-run this target in 32 bits
 
@@ -103,6 +104,41 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
+}
+
+// One residue code of the paired stream, zero-extended by the load itself (a 16-bit load of both codes costs
+// a mask, a second mask and a shift on the integer pipe per step; two byte loads cost nothing there).
+__device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p) {
+    uint32_t v;
+    asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// a * m + b with m a run-time 0 / 1: a select issued as one IMAD on the FMA pipe instead of a compare and a
+// SEL on the integer pipe, where they would compete with the DPX instructions.
+__device__ __forceinline__ uint32_t blend_fma(uint32_t a, uint32_t m, uint32_t b) { return a * m + b; }
+
+// kFlavorSWEndFast, end of a column: where a half-word of `best` changed, latch the column and the key (its low
+// bits name the row); then saturate the row bits.  Two LOP3 with predicate outputs, four SEL and one OR (ptxas turns
+// predicated moves and multiplies alike into SEL); the row is extracted from the latched key once, after the sweep.
+__device__ __forceinline__ uint32_t latch_key_s16x2(uint32_t best, uint32_t before, int c, int& colLo, int& colHi,
+                                                    uint32_t& keyLo, uint32_t& keyHi) {
+    uint32_t out;
+    asm("{.reg .pred pl, ph;\n\t"
+        ".reg .b32 x, l, h;\n\t"
+        "xor.b32 x, %5, %6;\n\t"
+        "and.b32 l, x, 0xffff;\n\t"
+        "and.b32 h, x, 0xffff0000;\n\t"
+        "setp.ne.u32 pl, l, 0;\n\t"
+        "setp.ne.u32 ph, h, 0;\n\t"
+        "@pl mov.b32 %1, %7;\n\t"
+        "@ph mov.b32 %2, %7;\n\t"
+        "@pl mov.b32 %3, %5;\n\t"
+        "@ph mov.b32 %4, %5;\n\t"
+        "or.b32 %0, %5, 0x003f003f;}\n\t"
+        : "=&r"(out), "+r"(colLo), "+r"(colHi), "+r"(keyLo), "+r"(keyHi)
+        : "r"(best), "r"(before), "r"(c));
+    return out;
 }
 
 // Packed max with per-half "a is still the max" predicates (a >= b).
@@ -168,6 +204,7 @@ struct Packed16 {
     static __device__ __forceinline__ reg bmax(reg a, reg b, bool* phi, bool* plo) { return vibmax_s16x2(a, b, phi, plo); }
     static __device__ __forceinline__ reg track(reg best, reg x, int& rowLo, int& rowHi, int row, int one) { return vimax_track_s16x2(best, x, rowLo, rowHi, row, one); }
     static __device__ __forceinline__ reg combine(uint32_t lo, uint32_t hi) { return lo + hi; }
+    static __device__ __forceinline__ reg blend(reg a, uint32_t m, reg b) { return blend_fma(a, m, b); }
 };
 
 struct Scalar32 {
@@ -190,6 +227,7 @@ struct Scalar32 {
         return v;
     }
     static __device__ __forceinline__ reg combine(uint32_t lo, uint32_t) { return (int)lo; }
+    static __device__ __forceinline__ reg blend(reg a, uint32_t m, reg b) { return (int)blend_fma((uint32_t)a, m, (uint32_t)b); }
 };
 
 // Column -1 of the DP matrix (reference src/opal.cpp:247-249 for SW, :671-679 for the others);
@@ -250,10 +288,8 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
     const uint32_t rowBytes = 4u * (uint32_t)p.rowStride;
     const reg negGe = TR::splat(-Ge), negGo = TR::splat(-Go), negGmin = TR::splat(-min(Ge, Go));
     const reg NEGV = TR::splat(TR::NEG);
-    // Keeping P[] live across steps and reloading each chunk for the next column right after its use was
-    // measured slower on B200 (0.83 vs 0.75 ms on BASELINE configs[1]: extra registers, no shorter step) and
-    // is incompatible with skipped idle columns, so it stays off; the code path is kept for re-evaluation.
-    constexpr bool kPrefetchP = false;
+    // (Keeping P[] live across steps and reloading each chunk for the next column right after its use was
+    // measured slower on B200: 0.83 vs 0.75 ms on BASELINE configs[1], extra registers and no shorter step.)
     // rows 4v .. 4v+3 (fewer at the tail) of one profile column: LDS.128 / .64 / .32 per plane
     auto load_chunk = [&](reg* P, uint32_t plo, uint32_t phi, int v) {
         const int j0 = v * 4;
@@ -280,6 +316,11 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
     // NW keeps padding at the bottom, so its last query row sits at a run-time position.
     const int lastRowPadded = p.Q - 1 + p.padTop;
     const int tLast = (lastRowPadded - p.rowBase) / R, jLast = (lastRowPadded - p.rowBase) % R;
+    // Thread 0 of a group has no thread above it: what enters its strip is row -1 of the matrix (first pass) or
+    // the previous pass's boundary row.  notFirst = 0 / 1 blends that in with an IMAD (see blend_fma); the value
+    // blended in is kept at 0 in every other thread.
+    const uint32_t notFirst = t != 0 ? (uint32_t)p.one : 0u;
+    const reg synIdle = t == 0 ? (kSW ? negGo : NEGV) : TR::splat(0);  // boundary row beyond the target's end
 
     // Work distribution: tasks are ordered longest first.  The first task of every warp is static and
     // strided so that the longest targets land on different SMs / scheduler partitions (warp w of
@@ -325,9 +366,15 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
         reg diag, outH, outF;  // outH/outF: bottom of this strip = (H - Go of its last row, F entering the row below)
         reg best;              // SW: running max of H (fast flavor: of the key H << 6 | 63 - row); global: H - Go of the last row
         int rowLo, rowHi, colLo, colHi;          // SW end / HW-OV last-row column
+        uint32_t keyLo, keyHi;                   // kFlavorSWEndFast: `best` as it was when the half-word last improved
         int nwScore[2], lcScore[2], lcRow[2];    // NW final cell; OV last column
         const reg* bH = reinterpret_cast<const reg*>(p.bndInH) + off0;  // boundary rows of the previous pass
         const reg* bF = reinterpret_cast<const reg*>(p.bndInF) + off0;
+        reg* oH = reinterpret_cast<reg*>(p.bndOutH) + off0;  // ... and of this pass
+        reg* oF = reinterpret_cast<reg*>(p.bndOutF) + off0;
+        // opaque to the compiler: otherwise it re-derives base + (off0 + c) * 4 in every step with seven integer-pipe
+        // instructions, stores predicated off or not; as plain pointers the address is one IMAD.WIDE each
+        asm volatile("" : "+l"(oH), "+l"(oF));
         reg nextBH, nextBF;
         auto init_state = [&](bool keyTracking) {
 #pragma unroll
@@ -339,11 +386,21 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
             outH = kSW ? negGo : NEGV; outF = outH;
             best = TR::splat(keyTracking ? (1 << kRowBits) - 1 : (kSW ? 0 : TR::NEG));
             rowLo = rowHi = colLo = colHi = -1;
+            keyLo = keyHi = 0;
             nwScore[0] = nwScore[1] = lcScore[0] = lcScore[1] = kScoreNone;
             lcRow[0] = lcRow[1] = -1;
-            nextBH = kSW ? negGo : NEGV; nextBF = nextBH;
+            nextBH = synIdle; nextBF = synIdle;
             if (!firstPass && t == 0 && Tmax > 0) { nextBH = bH[0]; nextBF = bF[0]; }
         };
+        unsigned storeLimit = (!lastPass && t == G - 1) ? (unsigned)Tmax : 0u;  // columns whose bottom row is parked
+        // OV: column of the shorter member's last-column scan inside the sweep (see below), -2 = none
+        int ovScanCol = (FLAVOR == kFlavorGlobal && mode == kModeOV && LANES == 2 && T[1] != T[0]) ? T[1] - 1 : -2;
+        // NW: column(s) whose cell in the last query row is the result; only the thread that holds that row looks
+        int nwCol[2] = {-2, -2};
+        if (FLAVOR == kFlavorGlobal && mode == kModeNW && lastPass && t == tLast) { nwCol[0] = T[0] - 1; nwCol[1] = T[1] - 1; }
+        // kept opaque so that each test stays ONE integer-pipe compare per step instead of being re-derived from
+        // its ingredients (pass, thread, mode, lengths) with three or four
+        asm volatile("" : "+r"(storeLimit), "+r"(ovScanCol), "+r"(nwCol[0]), "+r"(nwCol[1]));
 
         // OV: best cell of the last target column among this thread's rows (first row on ties), half-word l
         auto scan_last_column = [&](int l) {
@@ -354,23 +411,32 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
                 if (r >= 0 && r < p.Q && v > lcScore[l]) { lcScore[l] = v; lcRow[l] = r; }
             }
         };
-        // residues of column cc as (y0 + 1) | (y1 + 1) << 8, 0 = none.  The paired stream is padded, so
+        // residues of column cc as y0 + 1 and y1 + 1, 0 = none.  The paired stream is padded, so
         // only the upper clamp is needed (a group may idle while longer groups of its warp finish).
-        auto fetch = [&](int cc) -> uint32_t {
-            if (LANES == 2) return ps[min(cc, Tmax)];
-            return (cc >= 0 && cc < Tmax) ? (uint32_t)seq0[cc] + 1u : 0u;
+        struct Letters { uint32_t lo, hi; };
+        auto fetch = [&](int cc) -> Letters {
+            Letters w;
+            if (LANES == 2) {
+                const uint8_t* q = reinterpret_cast<const uint8_t*>(ps + min(cc, Tmax));
+                w.lo = ldg_u8(q); w.hi = ldg_u8(q + 1);
+            } else {
+                w.lo = (cc >= 0 && cc < Tmax) ? (uint32_t)seq0[cc] + 1u : 0u; w.hi = 0;
+            }
+            return w;
         };
         // One sweep of the task with tracking flavor TRACK (kFlavorSWEndFast tasks whose score leaves the exact
         // range of the key are swept a second time with kFlavorSWEnd, see below).
         auto sweep = [&](auto trackTag) {
             constexpr int TRACK = decltype(trackTag)::value;
             int c = -t;
-            uint32_t wnext = fetch(c);
+            Letters wnext = fetch(c);
             reg P[R];
-            if (kPrefetchP) {
-                const uint32_t plo0 = myLo + (wnext & 0xffu) * rowBytes, phi0 = myHi + (wnext >> 8) * rowBytes;
-    #pragma unroll
-                for (int v = 0; v < (R + 3) / 4; v++) load_chunk(P, plo0, phi0, v);
+            // row -1 of the matrix as seen by thread 0 (reference src/opal.cpp:716-732; all zeros for SW); NW's
+            // -Go - c * Ge walks down by Ge per column
+            reg synRow = TR::splat(0), synStep = TR::splat(0);
+            if (t == 0) {
+                synRow = negGo;  // H = 0 in row -1 (SW, HW, OV)
+                if (!kSW && mode == kModeNW) { synRow = TR::splat(-Go - Go); synStep = negGe; }
             }
 
             for (int s = 0; s < steps; s++, c++) {
@@ -382,20 +448,20 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
                     // costs more than the whole exchange.
                     reg synH, synF;
                     if (firstPass) {
-                        if (kSW) synH = negGo;  // row -1 is all zeros
-                        else synH = TR::splat((mode == kModeNW ? -Go - c * Ge : 0) - Go);  // row -1, reference :716-732
+                        synH = synRow;
                         synF = synH;  // F entering row 0 = max(-inf - Ge, H[-1][c] - Go)
+                        if (!kSW) synRow = TR::add(synRow, synStep);
                     } else {
                         synH = nextBH; synF = nextBF;
-                        nextBH = kSW ? negGo : NEGV; nextBF = nextBH;
+                        nextBH = synIdle; nextBF = synIdle;
                         if (t == 0 && c + 1 < Tmax) { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
                     }
-                    upH = (t == 0) ? synH : upH;
-                    upF = (t == 0) ? synF : upF;
+                    upH = TR::blend(upH, notFirst, synH);
+                    upF = TR::blend(upF, notFirst, synF);
                 }
-                const uint32_t wcur = wnext;
+                const Letters wcur = wnext;
                 wnext = fetch(c + 1);
-                const bool active = c >= 0 && c < Tmax;
+                const bool active = (unsigned)c < (unsigned)Tmax;
                 // SW runs its idle columns too: with the "no residue" letter they leave a state that is
                 // equivalent to the initial one (H = 0, negative E/F never matter) and cannot raise best.
                 if (!kSW && !active) continue;
@@ -409,12 +475,10 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
                 // Profile values of this column.  Short strips (R <= 20) keep P[] live across steps and reload each
                 // 4-row chunk for the NEXT column as soon as it has been consumed, which takes the shared-memory
                 // latency off the critical path of a warp that runs alone on its scheduler partition.
-                const uint32_t plo = myLo + (wcur & 0xffu) * rowBytes, phi = myHi + (wcur >> 8) * rowBytes;
-                const uint32_t ploNext = myLo + (wnext & 0xffu) * rowBytes, phiNext = myHi + (wnext >> 8) * rowBytes;
-                if (!kPrefetchP) load_chunk(P, plo, phi, 0);
+                const uint32_t plo = myLo + wcur.lo * rowBytes, phi = myHi + wcur.hi * rowBytes;
+                load_chunk(P, plo, phi, 0);
                 auto consumed = [&](int row) {  // P[row] has just been used
-                    if (kPrefetchP) { if (row % 4 == 3 || row == R - 1) load_chunk(P, ploNext, phiNext, row / 4); }
-                    else if (row % 4 == 3 && row + 1 < R) load_chunk(P, plo, phi, row / 4 + 1);
+                    if (row % 4 == 3 && row + 1 < R) load_chunk(P, plo, phi, row / 4 + 1);
                 };
                 reg f = upF;
                 const reg dIn = diag;
@@ -459,18 +523,15 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
                 if (TRACK == kFlavorSWEndFast) {
                     // A changed half-word means a strictly larger (score, first row) in THIS column: latch row and
                     // column, then saturate the row bits so that equal scores of later columns cannot win.
-                    const uint32_t b = (uint32_t)best, ch = b ^ (uint32_t)bestBefore;
-                    const int mask = (1 << kRowBits) - 1;
-                    if (ch & 0xffffu) { colLo = c; rowLo = mask - (int)(b & mask); }
-                    if (ch >> 16) { colHi = c; rowHi = mask - (int)((b >> 16) & mask); }
-                    best = (reg)(b | (uint32_t)mask * 0x00010001u);
+                    if constexpr (LANES == 2)
+                        best = latch_key_s16x2(best, bestBefore, c, colLo, colHi, keyLo, keyHi);
                 }
                 if (FLAVOR == kFlavorGlobal) {
                     if (mode == kModeNW) {
-                        if (lastPass && t == tLast) {
+                        {
     #pragma unroll
                             for (int l = 0; l < LANES; l++)
-                                if (c == T[l] - 1) {
+                                if (c == nwCol[l]) {
                                     reg v = HG[0];
     #pragma unroll
                                     for (int j = 1; j < R; j++) if (j == jLast) v = HG[j];
@@ -483,7 +544,8 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
                         // around them.  The shorter member of a pair needs no mask in the columns past its end: a
                         // cell there is reached through a horizontal gap from its last real column, so it is
                         // strictly below the value that column already contributed.
-                        if (lastPass) {
+                        // (Earlier passes run it as well; their result is never read.)
+                        {
                             bool ph, pl;
                             best = TR::bmax(best, u, &ph, &pl);
                             if (!pl) colLo = c;
@@ -494,14 +556,12 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
                         // of its own (one active thread per scan); the longer member -- and the shorter one when
                         // the lengths are equal, the usual case in a large sorted database -- is still sitting in
                         // HG[] when the sweep ends and is scanned there by all threads at once.
-                        if (mode == kModeOV && LANES == 2 && T[1] != T[0] && c == T[1] - 1) scan_last_column(1);
+                        if (c == ovScanCol) scan_last_column(1);
                     }
                 }
-                if (!lastPass) {  // kernel-uniform: single-pass searches skip the boundary row entirely
-                    if (t == G - 1 && active) {
-                        reinterpret_cast<reg*>(p.bndOutH)[off0 + c] = outH;
-                        reinterpret_cast<reg*>(p.bndOutF)[off0 + c] = outF;
-                    }
+                if ((unsigned)c < storeLimit) {  // last thread of a group, every pass but the last: park the bottom row
+                    asm volatile("st.global.b32 [%0], %1;" :: "l"(oH + c), "r"(outH) : "memory");
+                    asm volatile("st.global.b32 [%0], %1;" :: "l"(oF + c), "r"(outF) : "memory");
                 }
             }
 
@@ -516,7 +576,11 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
                 if (kSW) {
                     sc = TR::lane(best, l);
                     if (keyTracking) sc >>= kRowBits;
-                    if ((FLAVOR == kFlavorSWEnd || FLAVOR == kFlavorSWEndFast) && sc > 0) { cc = l ? colHi : colLo; rr = myRow0 + (l ? rowHi : rowLo); }
+                    if ((FLAVOR == kFlavorSWEnd || FLAVOR == kFlavorSWEndFast) && sc > 0) {
+                        cc = l ? colHi : colLo;
+                        const int mask = (1 << kRowBits) - 1;
+                        rr = myRow0 + (keyTracking ? mask - (int)(((l ? keyHi >> 16 : keyLo)) & mask) : (l ? rowHi : rowLo));
+                    }
                 } else if (mode == kModeNW) {
                     sc = nwScore[l]; cc = T[l] - 1; rr = p.Q - 1;
                 } else {
