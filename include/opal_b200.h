@@ -100,6 +100,11 @@ int opalb200_db_search_topk(OpalB200Db* handle, const unsigned char query[], int
 void opalb200_db_last_stats(const OpalB200Db* handle, int* kernelLaunches, int* rerun32, int* G, int* R, int* passes,
                             int* warpsPerPartition, int* groups);
 
+/* Targets of the last search that were swept "folded": one target per warp, occupying both 16-bit lanes (its
+ * second half of the query rows rides 32 columns behind the first), which is how the few longest targets of a
+ * database -- each bounds the search time, being swept by a single warp -- are finished sooner. 0 = none. */
+int opalb200_db_last_folded(const OpalB200Db* handle);
+
 /*
  * Measures the packed-DPX issue rate of `device` with a register-only kernel running the SW cell
  * recurrence (6 s16x2 instructions per 2 cells): returns giga cell updates per second that the

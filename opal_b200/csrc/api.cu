@@ -283,6 +283,8 @@ void opalb200_db_last_stats(const OpalB200Db* h, int* kernelLaunches, int* rerun
     if (groups) *groups = s.groups;
 }
 
+int opalb200_db_last_folded(const OpalB200Db* h) { return reinterpret_cast<const DeviceDb*>(h)->stats().foldedTasks; }
+
 double opalb200_measure_dpx_peak(int device, double* threadInstrPerSec, float* ms) {
     DeviceGuard guard;
     return measure_dpx_peak(device, threadInstrPerSec, ms);

@@ -362,16 +362,36 @@ struct TaskLens {
 // Picks (G, R, passes, warps per scheduler partition) for a query of Q rows over `taskLens` (one entry
 // per task, longest first) on `numSMs` SMs, and returns the estimated cycles in *estCycles.
 //
-// Timing model (cycles), fitted to B200 runs (profiles/): the integer pipe retires one packed DPX
-// instruction per 2 cycles per partition and a cell pair costs ~5.5 of them (11 cycles per row ideal).
-// Measured: one warp alone on its partition takes 17.75 R + 104 cycles per step (exposed latencies);
-// two warps sharing a partition take 2 (12.8 R + 57) per step each.  Two bounds:
+// Timing model (cycles): the time of one wavefront step of a warp that shares its scheduler partition with k - 1
+// others, measured on B200 with tools/steptime_probe.py (kStepCycles below; the integer pipe retires one packed
+// DPX instruction per 2 cycles per partition and a cell pair costs ~5.5 of them, 11 cycles per row ideal -- one
+// warp alone is latency-bound far above that, three warps together come within 40 %).  Two bounds:
 //   throughput:  sum over warp-tasks of steps * stepTime / (partitions * k)
 //   tail:        the longest target's steps * stepTime  (it cannot be split across warps)
 // Small databases with a long tail (BASELINE configs[1]) are tail-bound and want G = 32 and k = 1;
-// large ones are throughput-bound and want fewer threads per target and k = 2.
+// large ones are throughput-bound and want k = 3.
+// kStepCycles[flavor class][k - 1][i] = cycles per step at R = kStepR[i]; class 0 = SW score + end, 1 = SW score,
+// 2 = NW / HW / OV.  Linear in between.
+static const int kStepR[7] = {4, 8, 9, 12, 17, 24, 33};
+static const double kStepCycles[3][3][7] = {
+    {{193, 260, 276, 287, 366, 479, 608}, {243, 349, 382, 418, 570, 745, 925}, {301, 468, 520, 574, 782, 1042, 1320}},
+    {{183, 203, 236, 270, 313, 418, 565}, {224, 281, 314, 399, 473, 620, 846}, {262, 382, 408, 539, 672, 896, 1193}},
+    {{289, 342, 347, 382, 425, 491, 598}, {333, 407, 423, 492, 605, 713, 918}, {390, 470, 514, 608, 762, 921, 1380}},
+};
+static double step_cycles(int flavorClass, int k, int R) {
+    const double* t = kStepCycles[flavorClass][std::min(std::max(k, 1), 3) - 1];
+    if (R <= kStepR[0]) return t[0] * (0.5 + 0.5 * R / kStepR[0]);
+    for (int i = 1; i < 7; i++)
+        if (R <= kStepR[i]) return t[i - 1] + (t[i] - t[i - 1]) * (R - kStepR[i - 1]) / (double)(kStepR[i] - kStepR[i - 1]);
+    return t[6] * R / kStepR[6];
+}
+// Resident warps per scheduler partition the kernels are compiled for (launch_bound_for in search_kernel.cuh).
+static int max_warps_per_partition(int mode, int R) { return launch_bound_for(mode == kModeSW ? 0 : kFlavorGlobal, R) / 128; }
+
+static thread_local int t_forceK = 0;  // development override (OPAL_B200_SPLIT): warps per partition of the bulk group
+
 static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo, size_t hi, int smemLimit, int numSMs, int mode,
-                          bool latencyClass, Geometry* out, double* estCycles) {
+                          bool latencyClass, int flavorClass, Geometry* out, double* estCycles, bool folded = false) {
     const int planes = lanes == 2 ? 2 : 1;
     const auto& tables = kernel_tables();
     double bestCost = 1e300;
@@ -380,23 +400,26 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
     const double maxLen = hi > lo ? tl.len[lo] : 0;
     auto consider = [&](size_t ti, int G, int k, bool forced) {
         const int R = tables[ti].R;
+        if (t_forceK > 0 && !latencyClass && k != t_forceK) return;
         const int Rpad = rpad_of(R);
         const int rowStride = (G * Rpad + 31) / 32 * 32;
         const size_t smem = (size_t)planes * (A + 1) * rowStride * 4;
         if (smem > (size_t)smemLimit) return;
-        const int rows = G * R;
+        const int rows = (folded ? 2 : 1) * G * R;  // a folded task has its second 32 R rows in the high half-words
         const int passes = (Q + rows - 1) / rows;
+        if (folded && passes > 1) return;
         const int groupsPerWarp = 32 / G;
+        if (lo % groupsPerWarp) return;  // a warp takes groupsPerWarp consecutive tasks (and TaskLens::strided wants it so)
         // a warp-task lasts as long as its longest group: every groupsPerWarp-th task of the sorted list
         int sh = 0;
         while ((1 << sh) < groupsPerWarp) sh++;
         double warpTasks = 1;
         double warpSteps = tl.strided(sh, lo, hi, &warpTasks);
-        warpSteps += warpTasks * (G - 1);
+        warpSteps += warpTasks * (G - 1 + (folded ? kFoldLag : 0));
         warpTasks = std::max(1.0, warpTasks);
         // with fewer warp-tasks than resident warps the partitions are not shared k ways
-        const double kEff = std::max(1.0, std::min((double)k, std::ceil(warpTasks / (numSMs * 4.0))));
-        const double stepTime = kEff < 1.5 ? 17.75 * R + 104.0 : kEff * (12.8 * R + 57.0);
+        const int kEff = (int)std::max(1.0, std::min((double)k, std::ceil(warpTasks / (numSMs * 4.0))));
+        const double stepTime = step_cycles(flavorClass, kEff, R);
         const double warpsBusy = std::min((double)numSMs * 4 * k, warpTasks);
         double throughput = warpSteps * stepTime / warpsBusy;
         // Two warps share a partition only while both have work: with few tasks per warp a large part of the run is
@@ -406,7 +429,7 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
             const double tasksPerWarp = warpTasks / ((double)numSMs * 4 * k);
             if (tasksPerWarp < 3.5) throughput *= 1.0 + 0.3 * (3.5 - std::max(tasksPerWarp, 1.0));
         }
-        const double tail = (maxLen + G - 1) * stepTime;
+        const double tail = (maxLen + G - 1 + (folded ? kFoldLag : 0)) * stepTime;
         // every further pass is a kernel of its own (drain, launch, boundary rows through HBM): measured ~4 % each
         const double cost = passes * (std::max(throughput, tail) + 0.15 * std::min(throughput, tail) + 30000.0) *
                             (1.0 + 0.04 * (passes - 1));
@@ -416,16 +439,17 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
             out->G = G; out->R = R; out->tableIndex = (int)ti; out->passes = passes; out->Rpad = Rpad;
             out->rowStride = rowStride; out->smemBytes = smem; out->warpsPerPartition = k;
             out->padTop = (mode == kModeNW) ? 0 : passes * rows - Q;
+            out->folded = folded;
         }
     };
     for (size_t ti = 0; ti < tables.size(); ti++)
         for (int G = latencyClass ? 32 : 1; G <= 32; G *= 2)
-            for (int k = 1; k <= (latencyClass ? 1 : kBlockThreads / 128); k *= 2) consider(ti, G, k, false);
+            for (int k = 1; k <= (latencyClass ? 1 : max_warps_per_partition(mode, tables[ti].R)); k++) consider(ti, G, k, false);
     // Development override: OPAL_B200_GEOMETRY="G,R,k" forces a geometry (ignored when it does not fit).
     if (const char* env = getenv("OPAL_B200_GEOMETRY")) {
         int G = 0, R = 0, k = 0;
         if (!latencyClass && sscanf(env, "%d,%d,%d", &G, &R, &k) == 3 && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && k >= 1 &&
-            k <= kBlockThreads / 128)
+            k <= max_warps_per_partition(mode, R))
             for (size_t ti = 0; ti < tables.size(); ti++)
                 if (tables[ti].R == R) consider(ti, G, k, true);
     }
@@ -471,6 +495,25 @@ static __global__ void pack_pairs_kernel(const uint8_t* residues, const long lon
     __syncthreads();
     // largest residue code seen: one global atomic per block, and only while it still raises the value
     if (threadIdx.x == 0 && blockMax > 0 && blockMax - 1 > *(volatile int*)maxCode) atomicMax(maxCode, blockMax - 1);
+}
+
+// Folded stream of the longest targets (see SearchParams::folded): entry c of target p, c in [0, T + 32), is
+// (res[c] + 1) | (res[c - 32] + 1) << 8 with 0 where the index falls outside the target; 32 zero entries before
+// the first target and after every target.  One thread per entry; at most kFoldTargets targets, found by a walk.
+static __global__ void pack_folded_kernel(const uint8_t* residues, const long long* offsets, const int* lengths, const long long* foldOffsets,
+                                          int numFold, long long entries, uint16_t* foldStream) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= entries) return;
+    int p = 0;
+    while (p + 1 < numFold && foldOffsets[p + 1] <= e) p++;
+    const long long c = e - foldOffsets[p];
+    const int T = lengths[p];
+    uint32_t word = 0;
+    if (c >= 0 && c < T + kFoldLag) {
+        if (c < T) word = (uint32_t)residues[offsets[p] + c] + 1u;
+        if (c >= kFoldLag) word |= ((uint32_t)residues[offsets[p] + c - kFoldLag] + 1u) << 8;
+    }
+    foldStream[e] = (uint16_t)word;
 }
 
 // ------------------------------------------------------------------ DeviceDb
@@ -597,18 +640,25 @@ DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed,
         // database goes up in a single copy once the gather is complete.)  The residues part stays as the host
         // copy the alignment stage replays against.  Paired stream: [32 zeros][pair 0 columns][32 zeros][pair 1 ...].
         d->numPairs_ = (n + 1) / 2;
+        // the longest targets also get a folded stream (an even number of them: the bulk keeps whole pairs)
+        d->numFold_ = getenv("OPAL_B200_NO_FOLD") ? 0 : std::min(n & ~1, kFoldTargets);
+        while (d->numFold_ > 0 && d->sortedLen_[d->numFold_ - 1] < kFoldMinLength) d->numFold_ -= 2;
+        d->numFold_ = std::max(d->numFold_, 0);
         const size_t nOff = (size_t)n + 1, nPair = (size_t)std::max(d->numPairs_, 1), nLen = (size_t)std::max(n, 1);
-        const size_t indexBytes = (sizeof(long long) * (nOff + nPair) + sizeof(int) * (nLen + 1) + 255) / 256 * 256;
+        const size_t nFold = (size_t)std::max(d->numFold_, 1);
+        const size_t indexBytes = (sizeof(long long) * (nOff + nPair + nFold) + sizeof(int) * (nLen + 1) + 255) / 256 * 256;
         const size_t bytes = indexBytes + (size_t)total + 64;
         if (!pinned_alloc((void**)&d->hBlock_, bytes)) return false;
         if (!device_alloc(device, (void**)&d->dBlock_, bytes)) return false;
         long long* hOff = reinterpret_cast<long long*>(d->hBlock_);
         long long* hPair = hOff + nOff;
-        int* hLen = reinterpret_cast<int*>(hPair + nPair);
+        long long* hFold = hPair + nPair;
+        int* hLen = reinterpret_cast<int*>(hFold + nFold);
         d->hResidues_ = d->hBlock_ + indexBytes;
         d->dOffsets_ = reinterpret_cast<long long*>(d->dBlock_);
         d->dPairOffsets_ = d->dOffsets_ + nOff;
-        d->dLengths_ = reinterpret_cast<int*>(d->dPairOffsets_ + nPair);
+        d->dFoldOffsets_ = d->dPairOffsets_ + nPair;
+        d->dLengths_ = reinterpret_cast<int*>(d->dFoldOffsets_ + nFold);
         d->dMaxCode_ = d->dLengths_ + nLen;
         d->dResidues_ = d->dBlock_ + indexBytes;
         memcpy(hOff, d->offsets_.data(), sizeof(long long) * nOff);
@@ -619,6 +669,10 @@ DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed,
         hPair[0] = 32;
         for (int p = 0; p < d->numPairs_; p++) { hPair[p] = entries; entries += d->sortedLen_[2 * p] + 32; }
         entries += 64;
+        long long foldEntries = 32;
+        hFold[0] = 32;
+        for (int p = 0; p < d->numFold_; p++) { hFold[p] = foldEntries; foldEntries += d->sortedLen_[p] + kFoldLag + 32; }
+        foldEntries += 64;
         uint8_t* staging = d->hResidues_;
         memset(staging + total, 0, 64);
         // Parts of about equal residue count, cut at sequence boundaries; each is uploaded as soon as it and all
@@ -681,6 +735,12 @@ DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed,
                                                                         d->numPairs_, entries, d->dPairStream_, d->dMaxCode_);
             CUDA_TRY(cudaGetLastError());
         }
+        if (d->numFold_ > 0) {
+            if (!device_alloc(device, (void**)&d->dFoldStream_, sizeof(uint16_t) * (size_t)foldEntries)) return false;
+            pack_folded_kernel<<<(unsigned)((foldEntries + 255) / 256), 256, 0, d->stream_>>>(d->dResidues_, d->dOffsets_, d->dLengths_,
+                                                                                           d->dFoldOffsets_, d->numFold_, foldEntries, d->dFoldStream_);
+            CUDA_TRY(cudaGetLastError());
+        }
         CUDA_TRY(cudaMemcpyAsync(d->hMaxCode_, d->dMaxCode_, sizeof(int), cudaMemcpyDeviceToHost, d->stream_));
         if (trace.on) CUDA_TRY(cudaEventRecord(d->evStop_, d->stream_));
         trace.mark("issue");
@@ -716,6 +776,7 @@ DeviceDb* DeviceDb::clone_context() {
     c->order_ = order_; c->pos_ = pos_; c->sortedLen_ = sortedLen_; c->offsets_ = offsets_;
     c->hResidues_ = hResidues_; c->dResidues_ = dResidues_; c->dOffsets_ = dOffsets_; c->dLengths_ = dLengths_;
     c->dPairStream_ = dPairStream_; c->dPairOffsets_ = dPairOffsets_; c->numPairs_ = numPairs_; c->maxCode_ = maxCode_;
+    c->dFoldStream_ = dFoldStream_; c->dFoldOffsets_ = dFoldOffsets_; c->numFold_ = numFold_;
     if (cudaSetDevice(device_) != cudaSuccess || !c->alloc_search_buffers()) { delete c; return nullptr; }
     return c;
 }
@@ -732,7 +793,7 @@ DeviceDb::~DeviceDb() {
     void* own[] = {dResults_, dArgs_, dBndH_, dBndF_};
     for (void* p : own) device_release(device_, p);
     if (ownsDb_) {
-        void* shared[] = {dBlock_, dPairStream_};
+        void* shared[] = {dBlock_, dPairStream_, dFoldStream_};
         for (void* p : shared) device_release(device_, p);
         pinned_release(hBlock_); pinned_release(hMaxCode_);
     }
@@ -764,7 +825,7 @@ struct DeviceDb::Group {
 // busy long after everything else has finished (the tail bound of pick_geometry) gets a "latency class":
 // its longest tasks run with 32 threads per task and one warp per scheduler partition on SMs of their own,
 // concurrently with the throughput-oriented bulk group on the remaining SMs.
-bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, int mode, std::vector<Group>* groups) {
+bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, int mode, int wantEnd, std::vector<Group>* groups) {
     if (list.empty()) return true;
     const int lanes = type == 0 ? 2 : 1;
     // Packed16 works on the pairs fixed at packing time (targets 2p, 2p+1): a pair runs if either member
@@ -783,31 +844,60 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
 
     Geometry gAll;
     double tAll = 0;
-    if (!pick_geometry(Q, A, lanes, tl, 0, nT, smemLimit_, numSMs_, mode, false, &gAll, &tAll)) return false;
+    const int flavorClass = mode == kModeSW ? (wantEnd ? 0 : 1) : 2;
+    if (!pick_geometry(Q, A, lanes, tl, 0, nT, smemLimit_, numSMs_, mode, false, flavorClass, &gAll, &tAll)) return false;
     // candidate splits: the m longest tasks form the latency class on smL SMs
     double bestT = tAll;
     size_t bestM = 0;
     int bestSm = 0;
     Geometry bestL, bestB;
+    // Folded variant of the latency class (SW at 16 bits): the 2 m longest TARGETS, one per warp in both half-words,
+    // which halves the rows per thread and with them the time of the longest target.  Needs the folded stream
+    // (built for the numFold_ longest targets) and every one of those targets wanted.
+    TaskLens tlFold;
+    size_t foldable = 0;
+    if (lanes == 2 && mode == kModeSW && numFold_ > 0 && !getenv("OPAL_B200_NO_FOLD")) {
+        while (foldable < (size_t)numFold_ && foldable < list.size() && list[foldable] == (int)foldable) foldable++;
+        tlFold.len.assign(sortedLen_.begin(), sortedLen_.begin() + foldable);
+        tlFold.build();
+    }
     if (!getenv("OPAL_B200_NO_SPLIT") && !getenv("OPAL_B200_GEOMETRY")) {
-        for (size_t m = 32; m * 2 <= nT && m <= 4096; m *= 2) {  // multiples of 32 keep every group size aligned
-            for (int div = 1; div <= 4; div *= 2) {
-                const int smL = (int)std::min<size_t>((m + 4 * div - 1) / (4 * div), (size_t)numSMs_ / 2);
-                if (smL < 1) continue;
-                Geometry gL, gB;
-                double tL = 0, tB = 0;
-                if (!pick_geometry(Q, A, lanes, tl, 0, m, smemLimit_, smL, mode, true, &gL, &tL)) continue;
-                if (!pick_geometry(Q, A, lanes, tl, m, nT, smemLimit_, numSMs_ - smL, mode, false, &gB, &tB)) continue;
-                const double t = std::max(tL, tB) + 3000.0;  // a second launch is not free
-                if (t < bestT * 0.97) { bestT = t; bestM = m; bestSm = smL; bestL = gL; bestB = gB; }
+        // Development override: OPAL_B200_SPLIT="m,SMs,folded,k" forces the latency class (m pairs on so many SMs,
+        // folded or not) and the bulk's warps per partition (0 = free).
+        int fm = -1, fsm = 0, fv = 0, fk = 0;
+        if (const char* env = getenv("OPAL_B200_SPLIT"))
+            if (sscanf(env, "%d,%d,%d,%d", &fm, &fsm, &fv, &fk) != 4) fm = -1;
+        t_forceK = fm >= 0 ? fk : 0;
+        for (size_t m = 4; m * 2 <= nT && m <= 4096; m *= 2) {  // (a bulk geometry that m does not align with is skipped)
+            for (int variant = 0; variant < 2; variant++) {
+                const size_t tasksL = variant ? 2 * m : m;
+                if (variant && tasksL > foldable) continue;
+                if (fm >= 0 && ((int)m != fm || variant != fv)) continue;
+                for (int div = 1; div <= 4; div *= 2) {
+                    int smL = (int)std::min<size_t>((tasksL + 4 * div - 1) / (4 * div), (size_t)numSMs_ / 2);
+                    if (fm >= 0) { if (div > 1) continue; smL = fsm; bestT = 1e300; }
+                    if (smL < 1) continue;
+                    Geometry gL, gB;
+                    double tL = 0, tB = 0;
+                    if (!pick_geometry(Q, A, lanes, variant ? tlFold : tl, 0, tasksL, smemLimit_, smL, mode, true, flavorClass, &gL, &tL, variant != 0)) continue;
+                    if (!pick_geometry(Q, A, lanes, tl, m, nT, smemLimit_, numSMs_ - smL, mode, false, flavorClass, &gB, &tB)) continue;
+                    const double t = std::max(tL, tB) + 3000.0;  // a second launch is not free
+                    if (t < bestT * 0.97) { bestT = t; bestM = m; bestSm = smL; bestL = gL; bestB = gB; }
+                }
             }
         }
+        t_forceK = 0;
     }
     auto add = [&](size_t lo, size_t hi, const Geometry& g, int maxBlocks, size_t otherSmem, double est) {
         Group grp;
         grp.type = type;
         grp.estCycles = est;
-        grp.tasks.assign(tasks.begin() + lo, tasks.begin() + hi);
+        if (g.folded) {  // tasks are the sorted targets 0 .. 2 hi - 1 themselves
+            grp.tasks.resize(2 * hi);
+            for (size_t k = 0; k < 2 * hi; k++) grp.tasks[k] = (int)k;
+        } else {
+            grp.tasks.assign(tasks.begin() + lo, tasks.begin() + hi);
+        }
         grp.g = g;
         grp.maxBlocks = maxBlocks;
         grp.smemBytes = g.smemBytes;
@@ -855,6 +945,7 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
         p.rowStride = g.rowStride; p.Rpad = g.Rpad;
         p.residues = dResidues_; p.offsets = dOffsets_; p.lengths = dLengths_;
         p.pairStream = dPairStream_; p.pairOffsets = dPairOffsets_; p.numTargets = n_;
+        if (g.folded) { p.folded = 1; p.pairStream = dFoldStream_; p.pairOffsets = dFoldOffsets_; stats_.foldedTasks = (int)grp.tasks.size(); }
         p.taskList = contiguous ? nullptr : taskListDevice;
         p.taskBase = contiguous && !grp.tasks.empty() ? grp.tasks[0] : 0;
         p.numTasks = (int)grp.tasks.size();
@@ -884,7 +975,7 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
     std::vector<Group> groups;
     PhaseTrace trace("run_classes");
     for (auto& c : classes)
-        if (!plan_class(c.first, *c.second, Q, A, mode, &groups)) return OPAL_B200_ERR_CUDA;
+        if (!plan_class(c.first, *c.second, Q, A, mode, wantEnd, &groups)) return OPAL_B200_ERR_CUDA;
     if (groups.empty()) return 0;
     trace.mark("plan");
     stats_.groups = (int)groups.size();
@@ -917,8 +1008,9 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
     }
     if (getenv("OPAL_B200_TRACE"))
         for (const Group& g : groups)
-            fprintf(stderr, "[opal-b200] group type=%d tasks=%zu longest=%d G=%d R=%d k=%d passes=%d blocks<=%d est=%.0f kcycles\n", g.type,
-                    g.tasks.size(), g.tasks.empty() ? 0 : sortedLen_[g.type == 0 ? 2 * g.tasks[0] : g.tasks[0]], g.g.G, g.g.R,
+            fprintf(stderr, "[opal-b200] group type=%d%s tasks=%zu longest=%d G=%d R=%d k=%d passes=%d blocks<=%d est=%.0f kcycles\n", g.type,
+                    g.g.folded ? " folded" : "", g.tasks.size(),
+                    g.tasks.empty() ? 0 : sortedLen_[g.type == 0 && !g.g.folded ? 2 * g.tasks[0] : g.tasks[0]], g.g.G, g.g.R,
                     g.g.warpsPerPartition, g.g.passes, g.maxBlocks, g.estCycles / 1e3);
     auto body = [&]() -> bool {
         size_t listOffset = 0;

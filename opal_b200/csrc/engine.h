@@ -12,6 +12,8 @@ namespace opalb200 {
 
 // Return codes shared with opal.h (OPAL_ERR_OVERFLOW / _NO_SIMD_SUPPORT / _INVALID_MODE).
 constexpr int OPAL_B200_ERR_OVERFLOW = 1, OPAL_B200_ERR_CUDA = 2, OPAL_B200_ERR_MODE = 3;
+// Folded stream: at most this many of the longest targets, none shorter than kFoldMinLength.
+constexpr int kFoldTargets = 128, kFoldMinLength = 256;
 
 // Kernel registry: one translation unit per strip height R (kernels_inst.cu compiled with
 // -DOPAL_R=<R>), each exporting a table indexed [type * 4 + flavor]; type 0 = Packed16, 1 = Scalar32.
@@ -24,10 +26,11 @@ const std::vector<KernelTable>& kernel_tables();
 struct Geometry {
     int G = 1, R = 0, tableIndex = 0, passes = 1, Rpad = 0, rowStride = 0, padTop = 0, warpsPerPartition = 4;
     size_t smemBytes = 0;
+    bool folded = false;  // one target per warp in both half-words (SearchParams::folded)
 };
 
 struct SearchStats {
-    int kernelLaunches = 0, rerun32 = 0, G = 0, R = 0, passes = 0, warpsPerPartition = 0, groups = 0;
+    int kernelLaunches = 0, rerun32 = 0, G = 0, R = 0, passes = 0, warpsPerPartition = 0, groups = 0, foldedTasks = 0;
 };
 
 // Device memory from the per-device block cache (engine.cu): recycled, not returned to the driver.
@@ -82,7 +85,7 @@ private:
     DeviceDb* clone_context();
     bool alloc_search_buffers();
     struct Group;
-    bool plan_class(int type, const std::vector<int>& list, int Q, int A, int mode, std::vector<Group>* groups);
+    bool plan_class(int type, const std::vector<int>& list, int Q, int A, int mode, int wantEnd, std::vector<Group>* groups);
     bool launch_group(const Group& grp, int* taskListDevice, cudaStream_t stream, const unsigned char* dQuery, const int* dMatrix,
                       int Q, int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot);
     int run_classes(const std::vector<std::pair<int, const std::vector<int>*>>& classes, const unsigned char* dQuery,
@@ -104,6 +107,9 @@ private:
     uint32_t *dBndH_ = nullptr, *dBndF_ = nullptr;
     uint16_t* dPairStream_ = nullptr;
     long long* dPairOffsets_ = nullptr;
+    uint16_t* dFoldStream_ = nullptr;    // folded stream of the numFold_ longest targets
+    long long* dFoldOffsets_ = nullptr;
+    int numFold_ = 0;
     int *dMaxCode_ = nullptr, *hMaxCode_ = nullptr;
     unsigned char *hBlock_ = nullptr, *dBlock_ = nullptr;  // offsets | pair offsets | lengths | max code | residues (pinned / device)
     int numPairs_ = 0, maxCode_ = 0;

@@ -38,10 +38,11 @@
 
 namespace opalb200 {
 
-constexpr int kBlockThreads = 256;  // at most 2 warps per scheduler partition: measured as fast as 3 or 4
-// Register budget hint per flavor (measured on B200): the SW flavors schedule best when ptxas is capped at 170
-// registers (launch bound 384), the NW/HW/OV flavor with the full 255 (launch bound 256).
-constexpr int launch_bound_for(int flavor) { return flavor == 2 ? 256 : 384; }
+// Threads per block the kernels are compiled for = 128 x the warps that may share a scheduler partition.  Three
+// warps per partition (cap of 170 registers) give 6 - 20 % more throughput than two (tools/steptime_probe.py); a
+// fourth adds nothing and would need a 128-register cap.  The NW/HW/OV flavor at the tallest strips needs more
+// than 170 registers and stays at two.
+constexpr int launch_bound_for(int flavor, int R) { return (flavor == 2 && R > 24) ? 256 : 384; }
 constexpr int kModeNW = 0, kModeHW = 1, kModeOV = 2, kModeSW = 3;
 constexpr int kFlavorSWScore = 0, kFlavorSWEnd = 1, kFlavorGlobal = 2, kFlavorSWEndFast = 3;
 constexpr int kRowBits = 6;  // kFlavorSWEndFast: low bits of the tracked key hold 63 - row (latch_key_s16x2 spells the mask out)
@@ -88,7 +89,16 @@ struct SearchParams {
     int one;            // the constant 1, opaque to the compiler (see vimax_track_s16x2)
     int keyScale;       // 1 << kRowBits, opaque to the compiler so that the key is built by an IMAD (FMA pipe)
     int fastEndLimit;   // kFlavorSWEndFast: tracked scores at or above this are re-run by the exact flavor
+    // Folded tasks (SW, Packed16, G = 32, one pass): ONE target occupies both half-words.  The low halves of the
+    // warp hold query rows [0, 32 R), the high halves rows [32 R, 64 R) of the SAME target 32 columns behind, so
+    // the warp is a 64-deep wavefront: what leaves the low half of thread 31 enters the high half of thread 0 one
+    // step later.  Half the rows per thread means a much shorter step -- this is how the longest targets of a
+    // database, which bound the time of a search (each is swept by one warp), are finished sooner.  Tasks are
+    // sorted-target indices; pairStream / pairOffsets then point at the folded stream, whose entry c of a
+    // target is (res[c] + 1) | (res[c - 32] + 1) << 8 over T + 32 columns, padded like a pair.
+    int folded;
 };
+constexpr int kFoldLag = 32;  // columns between the two halves of a folded task = depth of one warp's wavefront
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
@@ -250,7 +260,7 @@ __device__ __forceinline__ bool better(int s, int c, int r, int S, int C, int R)
 // holds the biased score of padded query row rowBase + t*R + j against that letter in its low
 // half-word (sign bits cleared); plane HI holds it shifted left by 16.
 template <int R, int FLAVOR, class TR>
-__global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(launch_bound_for(FLAVOR, R), 1) search_kernel(const SearchParams p) {
     typedef typename TR::reg reg;
     constexpr int LANES = TR::LANES;
     constexpr bool kSW = FLAVOR != kFlavorGlobal;
@@ -263,15 +273,22 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
     for (int idx = threadIdx.x; idx < planeWords; idx += blockDim.x) {
         const int row = idx / p.rowStride, pos = idx - row * p.rowStride;
         const int t = pos / p.Rpad, j = pos - t * p.Rpad;
-        int sc = Go;  // padding rows score 0 against everything (keeps H = 0 above the query)
+        int sc = Go, scHi = Go;  // padding rows score 0 against everything (keeps H = 0 above the query)
         if (t < G && j < R) {
             const int r = p.rowBase + t * R + j - p.padTop;
             if (r >= 0 && r < p.Q) sc = ((row > 0) ? p.matrix[(int)p.query[r] * A + row - 1] : p.padLetterScore) + Go;
             else if (row == 0) sc = p.padLetterScore + Go;
+            scHi = sc;
+            if (LANES == 2 && p.folded) {  // high half-words: the rows 32 R further down
+                const int r2 = r + 32 * R;
+                scHi = Go;
+                if (r2 >= 0 && r2 < p.Q) scHi = ((row > 0) ? p.matrix[(int)p.query[r2] * A + row - 1] : p.padLetterScore) + Go;
+                else if (row == 0) scHi = p.padLetterScore + Go;
+            }
         }
         if (LANES == 2) {
             smem[idx] = (uint32_t)sc & 0xffffu;
-            smem[planeWords + idx] = (uint32_t)sc << 16;
+            smem[planeWords + idx] = (uint32_t)scHi << 16;
         } else {
             smem[idx] = (uint32_t)sc;
         }
@@ -319,8 +336,14 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
     // Thread 0 of a group has no thread above it: what enters its strip is row -1 of the matrix (first pass) or
     // the previous pass's boundary row.  notFirst = 0 / 1 blends that in with an IMAD (see blend_fma); the value
     // blended in is kept at 0 in every other thread.
-    const uint32_t notFirst = t != 0 ? (uint32_t)p.one : 0u;
-    const reg synIdle = t == 0 ? (kSW ? negGo : NEGV) : TR::splat(0);  // boundary row beyond the target's end
+    // Folded tasks: thread 0 takes the low half-word of thread 31 (delivered by the same rotating shuffle) into its
+    // high half-word -- a multiplication by 65536 -- and the boundary value only into its low half-word.
+    const bool folded = LANES == 2 && p.folded != 0;
+    const uint32_t notFirst = t != 0 ? (uint32_t)p.one : (folded ? 65536u * (uint32_t)p.one : 0u);
+    const uint32_t synMask = (t == 0 && folded) ? 0xffffu : 0xffffffffu;
+    const reg synIdle = t == 0 ? (reg)((uint32_t)(kSW ? negGo : NEGV) & synMask) : TR::splat(0);  // boundary row beyond the target's end
+    const int srcLane = (lane & ~(G - 1)) | ((t - 1) & (G - 1));  // the thread above; thread 0 reads the last thread
+    const int foldRows = folded ? 32 * R : 0;
 
     // Work distribution: tasks are ordered longest first.  The first task of every warp is static and
     // strided so that the longest targets land on different SMs / scheduler partitions (warp w of
@@ -347,8 +370,8 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
         if (taskIdx < p.numTasks) {
             const int task = p.taskList ? p.taskList[taskIdx] : p.taskBase + taskIdx;
             if (LANES == 2) {
-                tgt[0] = 2 * task;
-                tgt[1] = (2 * task + 1 < p.numTargets) ? 2 * task + 1 : -1;
+                tgt[0] = folded ? task : 2 * task;
+                tgt[1] = (!folded && 2 * task + 1 < p.numTargets) ? 2 * task + 1 : -1;
                 ps = p.pairStream + p.pairOffsets[task];
             } else {
                 tgt[0] = task;
@@ -358,7 +381,7 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
             off0 = p.offsets[tgt[0]];
             seq0 = p.residues + off0;
         }
-        const int Tmax = T[0];  // pairs are (longer, shorter)
+        const int Tmax = T[0] + ((folded && T[0] > 0) ? kFoldLag : 0);  // pairs are (longer, shorter); columns of the stream
         const int steps = __reduce_max_sync(0xffffffffu, Tmax > 0 ? Tmax + G - 1 : 0);
 
         // ---- per-thread DP state and tracking state; (re)initialised by init_state() to column -1
@@ -435,14 +458,17 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
             // -Go - c * Ge walks down by Ge per column
             reg synRow = TR::splat(0), synStep = TR::splat(0);
             if (t == 0) {
-                synRow = negGo;  // H = 0 in row -1 (SW, HW, OV)
+                synRow = (reg)((uint32_t)negGo & synMask);  // H = 0 in row -1 (SW, HW, OV)
                 if (!kSW && mode == kModeNW) { synRow = TR::splat(-Go - Go); synStep = negGe; }
             }
 
+#ifdef OPAL_UNROLL2
+#pragma unroll 2
+#endif
             for (int s = 0; s < steps; s++, c++) {
                 // ---- (H - Go, F) handed down by the row above, for column c
-                reg upH = __shfl_up_sync(0xffffffffu, outH, 1, G);
-                reg upF = __shfl_up_sync(0xffffffffu, outF, 1, G);
+                reg upH = __shfl_sync(0xffffffffu, outH, srcLane);
+                reg upF = __shfl_sync(0xffffffffu, outF, srcLane);
                 {   // thread 0 has no thread above: row -1 of the matrix (first pass) or the previous pass's
                     // boundary row.  Written as selects / predicated loads: a per-step divergent branch here
                     // costs more than the whole exchange.
@@ -580,6 +606,7 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
                         cc = l ? colHi : colLo;
                         const int mask = (1 << kRowBits) - 1;
                         rr = myRow0 + (keyTracking ? mask - (int)(((l ? keyHi >> 16 : keyLo)) & mask) : (l ? rowHi : rowLo));
+                        if (l == 1) { cc -= folded ? kFoldLag : 0; rr += foldRows; }  // folded: same target, 32 columns behind, 32 R rows down
                     }
                 } else if (mode == kModeNW) {
                     sc = nwScore[l]; cc = T[l] - 1; rr = p.Q - 1;
@@ -597,6 +624,7 @@ __global__ void __launch_bounds__(launch_bound_for(FLAVOR), 1) search_kernel(con
                 }
                 fsc[l] = sc; fcc[l] = cc; frr[l] = rr;
             }
+            if (LANES == 2 && folded && better(fsc[1], fcc[1], frr[1], fsc[0], fcc[0], frr[0])) { fsc[0] = fsc[1]; fcc[0] = fcc[1]; frr[0] = frr[1]; }
         };
 
         if (FLAVOR == kFlavorSWEndFast) {

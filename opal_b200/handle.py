@@ -46,6 +46,8 @@ class OpalB200(OpalCLibrary):
         L.opalb200_db_search.restype = ci
         L.opalb200_db_last_stats.argtypes = [vp] + [ctypes.POINTER(ci)] * 7
         L.opalb200_db_last_stats.restype = None
+        L.opalb200_db_last_folded.argtypes = [vp]
+        L.opalb200_db_last_folded.restype = ci
         L.opalb200_measure_dpx_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]
         L.opalb200_measure_dpx_peak.restype = ctypes.c_double
 
@@ -158,7 +160,9 @@ class ResidentDb:
     def last_stats(self):
         v = [ctypes.c_int(0) for _ in range(7)]
         self.eng.lib.opalb200_db_last_stats(self.handle, *[ctypes.byref(x) for x in v])
-        return dict(zip(("kernel_launches", "rerun32", "G", "R", "passes", "warps_per_partition", "groups"), (x.value for x in v)))
+        d = dict(zip(("kernel_launches", "rerun32", "G", "R", "passes", "warps_per_partition", "groups"), (x.value for x in v)))
+        d["folded"] = int(self.eng.lib.opalb200_db_last_folded(self.handle))
+        return d
 
     def close(self):
         if self.handle:

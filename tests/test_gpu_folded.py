@@ -1,0 +1,98 @@
+"""GPU parity of the folded sweep (SearchParams::folded in opal_b200/csrc/search_kernel.cuh): the longest targets of
+a database are swept one per warp with both 16-bit lanes on the SAME target -- the second half of the query rows
+rides 32 columns behind the first -- so that the targets which bound the search time finish sooner.  The databases
+here have a long tail so that the planner takes that route (asserted through opalb200_db_last_folded); every score and
+end location is compared with the oracle, and with the same search with folding switched off."""
+import os
+
+import numpy as np
+import pytest
+
+from _util import MODES, SequenceDB, search_dump
+from opal_b200 import datasets, matrices
+
+pytestmark = pytest.mark.gpu
+
+
+def _tailed_db(rng, sm, n_short, n_long, long_lo, long_hi, planted=None, planted_long=None):
+    seqs = [datasets.random_residues(int(x), rng, sm) for x in rng.integers(30, 420, n_short)]
+    longs = [datasets.random_residues(int(x), rng, sm) for x in rng.integers(long_lo, long_hi, n_long)]
+    if planted is not None:
+        for k in range(0, n_short, max(1, n_short // 6)):
+            seqs[k] = datasets.mutate(planted, 0.75, rng, sm)
+    if planted_long is not None:
+        # homologs INSIDE long targets, at both ends and in the middle, so that the best cell lies in either half
+        # of the query rows and on either side of the 32-column lag
+        for k in range(0, n_long, max(1, n_long // 5)):
+            t = longs[k]
+            h = datasets.mutate(planted_long, 0.9, rng, sm)
+            at = [0, max(0, len(t) - len(h)), len(t) // 3][(k // max(1, n_long // 5)) % 3]
+            t[at:at + len(h)] = h[:max(0, len(t) - at)]
+    order = rng.permutation(n_short + n_long)
+    allseqs = seqs + longs
+    return SequenceDB.from_sequences([allseqs[i] for i in order])
+
+
+def _check(product, oracle, q, db, go, ge, m, alen, st, expect_folded=True):
+    h = product.create_db(db, 0)
+    try:
+        rc, s, eq, et, _ = h.search(q, go, ge, m, alen, st, "SW")
+        assert rc == 0, product.last_error()
+        folded = h.last_stats()["folded"]
+        if expect_folded:
+            assert folded > 0, "planner did not fold the tail of this database"
+        rc, want = search_dump(oracle, q, db, go, ge, m, alen, st, MODES["SW"])
+        assert rc == 0
+        assert [int(x) for x in s] == [w[1] for w in want]
+        if st:
+            weq = [w[2] if w[1] > 0 else -1 for w in want]
+            wet = [w[3] if w[1] > 0 else -1 for w in want]
+            assert [int(x) for x in eq] == weq
+            assert [int(x) for x in et] == wet
+        return folded, (s.copy(), eq.copy(), et.copy())
+    finally:
+        h.close()
+
+
+@pytest.mark.parametrize("qlen", [97, 300, 513, 1100])
+@pytest.mark.parametrize("st", [0, 1])
+def test_folded_tail_matches_oracle(product, oracle, qlen, st):
+    rng = np.random.default_rng(100 + qlen)
+    sm = matrices.blosum62()
+    q = sm.encode(datasets.P18080)[:qlen] if qlen <= 513 else datasets.random_residues(qlen, rng, sm)
+    db = _tailed_db(rng, sm, 3000, 70, 2000, 5000, planted=q, planted_long=q)
+    # (a query much shorter than 64 x the smallest strip height is left to the ordinary latency class)
+    _check(product, oracle, q, db, 11, 1, sm.flat(), 23, st, expect_folded=qlen >= 300)
+
+
+def test_folded_matches_unfolded_and_overflow_reruns(product, oracle):
+    """8 x BLOSUM62 (gaps 88 / 8): planted near-copies inside long targets score above the 16-bit range, so folded
+    targets are flagged and re-run at 32 bits; scores between the key-tracking limit and the 16-bit limit take the
+    exact re-sweep inside the folded warp."""
+    rng = np.random.default_rng(7)
+    sm = matrices.blosum62()
+    m8 = (sm.flat() * 8).astype(np.int32)
+    q = datasets.random_residues(1000, rng, sm)
+    db = _tailed_db(rng, sm, 2500, 64, 3000, 6000, planted=q[:300], planted_long=q)
+    folded, got = _check(product, oracle, q, db, 88, 8, m8, 23, 1)
+    os.environ["OPAL_B200_NO_FOLD"] = "1"
+    try:
+        folded2, got2 = _check(product, oracle, q, db, 88, 8, m8, 23, 1, expect_folded=False)
+    finally:
+        del os.environ["OPAL_B200_NO_FOLD"]
+    assert folded2 == 0
+    for a, b in zip(got, got2):
+        assert np.array_equal(a, b)
+    assert int(got[0].max()) > 32767
+
+
+def test_folded_dna_zero_extension_gaps(product, oracle):
+    """Alphabet 4, gapExt 0 and a query shorter than one strip: ties everywhere, first-row / first-column rule."""
+    rng = np.random.default_rng(8)
+    sm = matrices.simple(4, 2, -3)
+    q = rng.integers(0, 4, 70).astype(np.uint8)
+    seqs = [rng.integers(0, 4, int(x)).astype(np.uint8) for x in rng.integers(20, 300, 4000)]
+    seqs += [rng.integers(0, 4, int(x)).astype(np.uint8) for x in rng.integers(3000, 9000, 66)]
+    db = SequenceDB.from_sequences(seqs)
+    for st in (0, 1):
+        _check(product, oracle, q, db, 3, 0, sm.flat(), 4, st, expect_folded=False)

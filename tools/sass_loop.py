@@ -3,7 +3,7 @@
 
 usage: tools/sass_loop.py opal_b200/csrc/build/kernels_R17.o [flavor=3] [arith=Packed16]
 
-For every innermost loop that contains SHFL.UP (the wavefront step) prints how many instructions of each
+For every innermost loop that holds the DPX recurrence (the wavefront step) prints how many instructions of each
 pipe class the straight-line body holds.  Classes follow the B200 measurements in profiles/README.md:
 the DPX / min-max / logic / compare / select / shift instructions issue on the 16-lane ALU pipe (the
 bottleneck of this kernel), IMAD* / VIADD on the FMA pipe, loads / stores / shuffles on the LSU.
@@ -54,9 +54,11 @@ def main():
         print(name)
         for lo, hi in loops:
             body = ins[lo:hi + 1]
-            if not any(op.startswith("SHFL.UP") for _, _, op, _ in body):
+            def is_sweep(b):
+                return sum(1 for _, _, op, _ in b if op.startswith("VIADDMNMX")) >= 8
+            if not is_sweep(body):
                 continue
-            if any(l2 > lo and h2 < hi and any(op.startswith("SHFL.UP") for _, _, op, _ in ins[l2:h2 + 1]) for l2, h2 in loops):
+            if any((l2 > lo or h2 < hi) and l2 >= lo and h2 <= hi and is_sweep(ins[l2:h2 + 1]) for l2, h2 in loops):
                 continue
             cls = Counter()
             ops = Counter()
