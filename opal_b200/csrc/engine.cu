@@ -376,7 +376,7 @@ static const int kStepR[7] = {4, 8, 9, 12, 17, 24, 33};
 static const double kStepCycles[3][3][7] = {
     {{193, 260, 276, 287, 366, 479, 608}, {243, 349, 382, 418, 570, 745, 925}, {301, 468, 520, 574, 782, 1042, 1320}},
     {{183, 203, 236, 270, 313, 418, 565}, {224, 281, 314, 399, 473, 620, 846}, {262, 382, 408, 539, 672, 896, 1193}},
-    {{289, 342, 347, 382, 425, 491, 598}, {333, 407, 423, 492, 605, 713, 918}, {390, 470, 514, 608, 762, 921, 1380}},
+    {{289, 342, 347, 382, 425, 491, 598}, {333, 407, 423, 492, 605, 713, 918}, {390, 470, 514, 608, 762, 921, 1240}},
 };
 static double step_cycles(int flavorClass, int k, int R) {
     const double* t = kStepCycles[flavorClass][std::min(std::max(k, 1), 3) - 1];
@@ -386,9 +386,12 @@ static double step_cycles(int flavorClass, int k, int R) {
     return t[6] * R / kStepR[6];
 }
 // Resident warps per scheduler partition the kernels are compiled for (launch_bound_for in search_kernel.cuh).
-static int max_warps_per_partition(int mode, int R) { return launch_bound_for(mode == kModeSW ? 0 : kFlavorGlobal, R) / 128; }
+// (The 32-bit NW/HW/OV kernels at the tallest strips exist only uncapped, for two.)
+static int max_warps_per_partition(int mode, int R, int lanes) {
+    return (lanes == 1 && mode != kModeSW) ? launch_bound_for(kFlavorGlobal, R) / 128 : 3;
+}
 
-static thread_local int t_forceK = 0;  // development override (OPAL_B200_SPLIT): warps per partition of the bulk group
+static thread_local int t_forceK = 0, t_forceG = 0, t_forceR = 0;  // development override (OPAL_B200_SPLIT): geometry of the bulk group
 
 static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo, size_t hi, int smemLimit, int numSMs, int mode,
                           bool latencyClass, int flavorClass, Geometry* out, double* estCycles, bool folded = false) {
@@ -398,9 +401,16 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
     bool found = false;
     const double tasks = (double)(hi - lo);
     const double maxLen = hi > lo ? tl.len[lo] : 0;
+    int minPasses = 1 << 20;  // fewest passes any geometry that fits shared memory needs
+    for (size_t ti = 0; ti < tables.size(); ti++)
+        for (int G = latencyClass ? 32 : 1; G <= 32; G *= 2) {
+            const int rows = (folded ? 2 : 1) * G * tables[ti].R;
+            const size_t smem = (size_t)planes * (A + 1) * ((G * rpad_of(tables[ti].R) + 31) / 32 * 32) * 4;
+            if (smem <= (size_t)smemLimit) minPasses = std::min(minPasses, (Q + rows - 1) / rows);
+        }
     auto consider = [&](size_t ti, int G, int k, bool forced) {
         const int R = tables[ti].R;
-        if (t_forceK > 0 && !latencyClass && k != t_forceK) return;
+        if (!latencyClass && ((t_forceK > 0 && k != t_forceK) || (t_forceG > 0 && G != t_forceG) || (t_forceR > 0 && R != t_forceR))) return;
         const int Rpad = rpad_of(R);
         const int rowStride = (G * Rpad + 31) / 32 * 32;
         const size_t smem = (size_t)planes * (A + 1) * rowStride * 4;
@@ -408,6 +418,12 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
         const int rows = (folded ? 2 : 1) * G * R;  // a folded task has its second 32 R rows in the high half-words
         const int passes = (Q + rows - 1) / rows;
         if (folded && passes > 1) return;
+        // more than a third of the swept rows padding: never the best choice unless nothing smaller exists (the
+        // planner runs on the path of every drop-in call, so hopeless candidates are dropped before they are priced)
+        if (!forced && (long long)passes * rows * 3 > (long long)Q * 4 + 96 && !(G == (latencyClass ? 32 : 1) && ti == 0)) return;
+        // more passes than the tallest geometry needs (one more for queries that take several anyway): the same
+        // cells plus boundary rows through HBM and further launches
+        if (!forced && passes > minPasses + (minPasses > 1 ? 1 + minPasses / 2 : 0)) return;
         const int groupsPerWarp = 32 / G;
         if (lo % groupsPerWarp) return;  // a warp takes groupsPerWarp consecutive tasks (and TaskLens::strided wants it so)
         // a warp-task lasts as long as its longest group: every groupsPerWarp-th task of the sorted list
@@ -429,6 +445,8 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
             const double tasksPerWarp = warpTasks / ((double)numSMs * 4 * k);
             if (tasksPerWarp < 3.5) throughput *= 1.0 + 0.3 * (3.5 - std::max(tasksPerWarp, 1.0));
         }
+        // (Measured on BASELINE configs[1]: with three warps on its partition the longest task advances at ~630 cycles
+        // per step of R = 17, with two at ~540 -- no faster than the table says, although it sits on the oldest warp.)
         const double tail = (maxLen + G - 1 + (folded ? kFoldLag : 0)) * stepTime;
         // every further pass is a kernel of its own (drain, launch, boundary rows through HBM): measured ~4 % each
         const double cost = passes * (std::max(throughput, tail) + 0.15 * std::min(throughput, tail) + 30000.0) *
@@ -444,12 +462,12 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
     };
     for (size_t ti = 0; ti < tables.size(); ti++)
         for (int G = latencyClass ? 32 : 1; G <= 32; G *= 2)
-            for (int k = 1; k <= (latencyClass ? 1 : max_warps_per_partition(mode, tables[ti].R)); k++) consider(ti, G, k, false);
+            for (int k = 1; k <= (latencyClass ? 1 : max_warps_per_partition(mode, tables[ti].R, lanes)); k++) consider(ti, G, k, false);
     // Development override: OPAL_B200_GEOMETRY="G,R,k" forces a geometry (ignored when it does not fit).
     if (const char* env = getenv("OPAL_B200_GEOMETRY")) {
         int G = 0, R = 0, k = 0;
         if (!latencyClass && sscanf(env, "%d,%d,%d", &G, &R, &k) == 3 && G >= 1 && G <= 32 && (G & (G - 1)) == 0 && k >= 1 &&
-            k <= max_warps_per_partition(mode, R))
+            k <= max_warps_per_partition(mode, R, lanes))
             for (size_t ti = 0; ti < tables.size(); ti++)
                 if (tables[ti].R == R) consider(ti, G, k, true);
     }
@@ -862,12 +880,12 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
         tlFold.build();
     }
     if (!getenv("OPAL_B200_NO_SPLIT") && !getenv("OPAL_B200_GEOMETRY")) {
-        // Development override: OPAL_B200_SPLIT="m,SMs,folded,k" forces the latency class (m pairs on so many SMs,
-        // folded or not) and the bulk's warps per partition (0 = free).
-        int fm = -1, fsm = 0, fv = 0, fk = 0;
+        // Development override: OPAL_B200_SPLIT="m,SMs,folded,k[,G,R]" forces the latency class (m pairs on so many
+        // SMs, folded or not) and the bulk's warps per partition / group size / strip height (0 = free).
+        int fm = -1, fsm = 0, fv = 0, fk = 0, fg = 0, fr = 0;
         if (const char* env = getenv("OPAL_B200_SPLIT"))
-            if (sscanf(env, "%d,%d,%d,%d", &fm, &fsm, &fv, &fk) != 4) fm = -1;
-        t_forceK = fm >= 0 ? fk : 0;
+            if (sscanf(env, "%d,%d,%d,%d,%d,%d", &fm, &fsm, &fv, &fk, &fg, &fr) < 4) fm = -1;
+        t_forceK = fm >= 0 ? fk : 0; t_forceG = fm >= 0 ? fg : 0; t_forceR = fm >= 0 ? fr : 0;
         for (size_t m = 4; m * 2 <= nT && m <= 4096; m *= 2) {  // (a bulk geometry that m does not align with is skipped)
             for (int variant = 0; variant < 2; variant++) {
                 const size_t tasksL = variant ? 2 * m : m;
@@ -886,7 +904,7 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
                 }
             }
         }
-        t_forceK = 0;
+        t_forceK = t_forceG = t_forceR = 0;
     }
     auto add = [&](size_t lo, size_t hi, const Geometry& g, int maxBlocks, size_t otherSmem, double est) {
         Group grp;
@@ -935,6 +953,8 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
                          !getenv("OPAL_B200_EXACT_END");
     const int flavor = (mode == kModeSW) ? (wantEnd ? (fastEnd ? kFlavorSWEndFast : kFlavorSWEnd) : kFlavorSWScore) : kFlavorGlobal;
     const void* fn = kernel_tables()[g.tableIndex].fn[type * 4 + flavor];
+    if (flavor == kFlavorGlobal && 128 * g.warpsPerPartition > launch_bound_for(flavor, g.R))
+        fn = kernel_tables()[g.tableIndex].fn[type == 0 ? 8 : type * 4 + flavor];  // Packed16 variant compiled for 384 threads
     CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grp.smemBytes));
     for (int pass = 0; pass < g.passes; pass++) {
         SearchParams p;

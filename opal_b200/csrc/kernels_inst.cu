@@ -8,7 +8,7 @@
 #define OPAL_CAT(a, b) OPAL_CAT2(a, b)
 
 namespace opalb200 {
-static const void* const kTable[8] = {
+static const void* const kTable[9] = {
     (const void*)search_kernel<OPAL_R, kFlavorSWScore, Packed16>,
     (const void*)search_kernel<OPAL_R, kFlavorSWEnd, Packed16>,
     (const void*)search_kernel<OPAL_R, kFlavorGlobal, Packed16>,
@@ -17,6 +17,7 @@ static const void* const kTable[8] = {
     (const void*)search_kernel<OPAL_R, kFlavorSWEnd, Scalar32>,
     (const void*)search_kernel<OPAL_R, kFlavorGlobal, Scalar32>,
     (const void*)search_kernel<OPAL_R, kFlavorSWEnd, Scalar32>,  // no fast variant at 32 bits
+    (const void*)search_kernel<OPAL_R, kFlavorGlobal, Packed16, 384>,  // three warps per partition (170-register cap)
 };
 const void* const* OPAL_CAT(kernel_table_R, OPAL_R)() { return kTable; }
 }  // namespace opalb200

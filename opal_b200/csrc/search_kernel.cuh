@@ -40,8 +40,9 @@ namespace opalb200 {
 
 // Threads per block the kernels are compiled for = 128 x the warps that may share a scheduler partition.  Three
 // warps per partition (cap of 170 registers) give 6 - 20 % more throughput than two (tools/steptime_probe.py); a
-// fourth adds nothing and would need a 128-register cap.  The NW/HW/OV flavor at the tallest strips needs more
-// than 170 registers and stays at two.
+// fourth adds nothing and would need a 128-register cap.  The NW/HW/OV flavor at the tallest strips wants more
+// than 170 registers: it is compiled twice, uncapped for one or two warps per partition (where the cap costs up to
+// 25 %) and capped for three (+10 % throughput over two uncapped).
 constexpr int launch_bound_for(int flavor, int R) { return (flavor == 2 && R > 24) ? 256 : 384; }
 constexpr int kModeNW = 0, kModeHW = 1, kModeOV = 2, kModeSW = 3;
 constexpr int kFlavorSWScore = 0, kFlavorSWEnd = 1, kFlavorGlobal = 2, kFlavorSWEndFast = 3;
@@ -259,8 +260,8 @@ __device__ __forceinline__ bool better(int s, int c, int r, int S, int C, int R)
 // Row 0 is the "no residue" letter, row y+1 is target letter y.  Word (row, t*Rpad + j) of plane LO
 // holds the biased score of padded query row rowBase + t*R + j against that letter in its low
 // half-word (sign bits cleared); plane HI holds it shifted left by 16.
-template <int R, int FLAVOR, class TR>
-__global__ void __launch_bounds__(launch_bound_for(FLAVOR, R), 1) search_kernel(const SearchParams p) {
+template <int R, int FLAVOR, class TR, int MAXT = launch_bound_for(FLAVOR, R)>
+__global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
     typedef typename TR::reg reg;
     constexpr int LANES = TR::LANES;
     constexpr bool kSW = FLAVOR != kFlavorGlobal;
