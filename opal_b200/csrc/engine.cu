@@ -378,12 +378,18 @@ static const double kStepCycles[3][3][7] = {
     {{183, 203, 236, 270, 313, 418, 565}, {224, 281, 314, 399, 473, 620, 846}, {262, 382, 408, 539, 672, 896, 1193}},
     {{289, 342, 347, 382, 425, 491, 598}, {333, 407, 423, 492, 605, 713, 918}, {390, 470, 514, 608, 762, 921, 1240}},
 };
-static double step_cycles(int flavorClass, int k, int R) {
+static double step_cycles_lockstep(int flavorClass, int k, int R) {
     const double* t = kStepCycles[flavorClass][std::min(std::max(k, 1), 3) - 1];
     if (R <= kStepR[0]) return t[0] * (0.5 + 0.5 * R / kStepR[0]);
     for (int i = 1; i < 7; i++)
         if (R <= kStepR[i]) return t[i - 1] + (t[i] - t[i - 1]) * (R - kStepR[i - 1]) / (double)(kStepR[i] - kStepR[i - 1]);
     return t[6] * R / kStepR[6];
+}
+// The table was taken with all warps of a partition in lockstep (equal tasks started together), the worst case for
+// pipe contention; with tasks of mixed lengths the same probe measures 7 / 5 / 1.5 % less for k = 1 / 2 / 3.
+static const double kStepMixed[3] = {0.93, 0.95, 0.985};
+static double step_cycles(int flavorClass, int k, int R) {
+    return kStepMixed[std::min(std::max(k, 1), 3) - 1] * step_cycles_lockstep(flavorClass, k, R);
 }
 // Resident warps per scheduler partition the kernels are compiled for (launch_bound_for in search_kernel.cuh).
 // (The 32-bit NW/HW/OV kernels at the tallest strips exist only uncapped, for two.)
@@ -447,9 +453,11 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
         }
         // (Measured on BASELINE configs[1]: with three warps on its partition the longest task advances at ~630 cycles
         // per step of R = 17, with two at ~540 -- no faster than the table says, although it sits on the oldest warp.)
-        const double tail = (maxLen + G - 1 + (folded ? kFoldLag : 0)) * stepTime;
+        // A launch takes the longer of the two plus a little of the other (fitted on forced splits of BASELINE
+        // configs[1], tools/split_sweep.sh: within 6 % of the measured time for latency classes of 8 - 128 targets).
+        const double tail = 0.95 * (maxLen + G - 1 + (folded ? kFoldLag : 0)) * stepTime;
         // every further pass is a kernel of its own (drain, launch, boundary rows through HBM): measured ~4 % each
-        const double cost = passes * (std::max(throughput, tail) + 0.15 * std::min(throughput, tail) + 30000.0) *
+        const double cost = passes * (std::max(throughput, tail) + 0.05 * std::min(throughput, tail) + 30000.0) *
                             (1.0 + 0.04 * (passes - 1));
         if (forced || cost < bestCost) {
             bestCost = cost;
