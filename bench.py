@@ -279,8 +279,10 @@ def run_b200_arm(args, rank, local_rank, world):
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = total_cells / 1e9 / t_e2e
-    # one upload block [offsets | pair offsets | lengths | max code | residues] + one argument block [counters | matrix | query]
-    index_bytes = (8 * (len(db) + 1) + 8 * max((len(db) + 1) // 2, 1) + 4 * (max(len(db), 1) + 1) + 255) // 256 * 256
+    # one upload block [offsets | pair offsets | fold offsets | lengths | max code | residues] + one argument block
+    # [counters | matrix | query]; the folded stream of the longest targets is built on the device (at most 128 offsets go up)
+    n_fold = max(min(len(db) & ~1, 128), 1)
+    index_bytes = (8 * (len(db) + 1) + 8 * max((len(db) + 1) // 2, 1) + 8 * n_fold + 4 * (max(len(db), 1) + 1) + 255) // 256 * 256
     h2d = int(index_bytes + db.total_residues + 64 + 1024 + (4 * A * A + 255) // 256 * 256 + Q + 16)
     d2h = int(3 * 4 * len(db) + 4)
 
@@ -335,7 +337,7 @@ def run_b200_arm(args, rank, local_rank, world):
                 "config": {"workload": desc, "mode": MODE, "search": "score+end", "query_length": Q,
                            "db_sequences_per_gpu": len(db), "db_residues_per_gpu": db.total_residues,
                            "l2": "256 MiB flush buffer written between timed steps",
-                           "geometry": {k: stats[k] for k in ("G", "R", "passes", "warps_per_partition")}},
+                           "geometry": {k: stats[k] for k in ("G", "R", "passes", "warps_per_partition", "groups", "folded")}},
                 "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": t_e2e / args.steps * 1e3, "path": "opalSearchDatabase (pack + H2D + kernels + D2H + records)"},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "multi_query": multi_query,

@@ -398,6 +398,10 @@ static int max_warps_per_partition(int mode, int R, int lanes) {
 }
 
 static thread_local int t_forceK = 0, t_forceG = 0, t_forceR = 0;  // development override (OPAL_B200_SPLIT): geometry of the bulk group
+// Several searches in flight (search_batch): the tail of one search overlaps the bulk of the next, so a plan is priced
+// mostly by the SM time it takes, not by when its last task ends.  Measured on BASELINE configs[1], 32 queries with
+// three in flight: plans with three warps per partition give 3975 - 4010 GCUPS, the single-search optimum 3770.
+static thread_local bool t_overlapped = false;
 
 static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo, size_t hi, int smemLimit, int numSMs, int mode,
                           bool latencyClass, int flavorClass, Geometry* out, double* estCycles, bool folded = false) {
@@ -455,7 +459,7 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
         // per step of R = 17, with two at ~540 -- no faster than the table says, although it sits on the oldest warp.)
         // A launch takes the longer of the two plus a little of the other (fitted on forced splits of BASELINE
         // configs[1], tools/split_sweep.sh: within 6 % of the measured time for latency classes of 8 - 128 targets).
-        const double tail = 0.95 * (maxLen + G - 1 + (folded ? kFoldLag : 0)) * stepTime;
+        const double tail = (t_overlapped ? 0.6 : 0.95) * (maxLen + G - 1 + (folded ? kFoldLag : 0)) * stepTime;
         // every further pass is a kernel of its own (drain, launch, boundary rows through HBM): measured ~4 % each
         const double cost = passes * (std::max(throughput, tail) + 0.05 * std::min(throughput, tail) + 30000.0) *
                             (1.0 + 0.04 * (passes - 1));
@@ -1278,8 +1282,10 @@ int DeviceDb::search_batch(int numQueries, const unsigned char* const* queries, 
     if (K == 1) worker(0);
     else {
         std::vector<std::thread> th;
-        for (int k = 1; k < K; k++) th.emplace_back(worker, k);
+        for (int k = 1; k < K; k++) th.emplace_back([&worker, k]() { t_overlapped = true; worker(k); });
+        t_overlapped = true;
         worker(0);
+        t_overlapped = false;
         for (auto& t : th) t.join();
     }
     event_release(device_, evBatch);

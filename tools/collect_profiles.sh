@@ -15,4 +15,7 @@ ncu -i $out/r1_search_kernel.ncu-rep --page raw 2>/dev/null | grep -E "search_ke
 QLENS=144,375,1000,2005,5478 MODES=SW,NW,HW,OV python tools/quick_perf.py config3 570000 > $out/r1_config3_table.txt 2>&1
 python tools/batch_probe.py config2 SW 1 32 > $out/r1_batch_probe.txt 2>&1
 python tools/batch_probe.py 570000 SW 1 20 >> $out/r1_batch_probe.txt 2>&1
+KS=1,2,3 python tools/steptime_probe.py 2000 > $out/r1_steptime_probe.txt 2>&1
+python tools/quick_perf.py config2 2>&1 | grep "type=\|DPX" > $out/r1_config2_table.txt
+OPAL_B200_TRACE=1 python tools/one_search.py config2 SW 1 2 2>&1 | grep "group" | tail -2 > $out/r1_config2_plan.txt
 ls -la $out
