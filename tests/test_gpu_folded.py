@@ -96,3 +96,34 @@ def test_folded_dna_zero_extension_gaps(product, oracle):
     db = SequenceDB.from_sequences(seqs)
     for st in (0, 1):
         _check(product, oracle, q, db, 3, 0, sm.flat(), 4, st, expect_folded=False)
+
+
+def test_folded_with_skipped_targets_and_batches(product, oracle):
+    """A skipped target among the longest ones leaves fewer foldable targets (the folded class takes a prefix of the
+    length-sorted database whose members are all wanted); a batch with several queries in flight shares the folded
+    stream between its search contexts.  Both must give what single full searches give."""
+    rng = np.random.default_rng(11)
+    sm = matrices.blosum62()
+    q = sm.encode(datasets.P18080)
+    db = _tailed_db(rng, sm, 3000, 70, 2000, 5000, planted=q, planted_long=q)
+    h = product.create_db(db, 0)
+    try:
+        rc, s0, eq0, et0, _ = h.search(q, 11, 1, sm.flat(), 23, 1, "SW")
+        assert rc == 0 and h.last_stats()["folded"] > 0
+        order = np.argsort(-db.lengths.astype(np.int64), kind="stable")
+        for skipped in ([int(order[0])], [int(order[5]), int(order[40])], [int(i) for i in order[:70]]):
+            skip = np.zeros(len(db), dtype=np.uint8)
+            skip[skipped] = 1
+            rc, s, eq, et, _ = h.search(q, 11, 1, sm.flat(), 23, 1, "SW", skip=skip)
+            assert rc == 0
+            keep = skip == 0
+            assert np.array_equal(s[keep], s0[keep]) and np.array_equal(eq[keep], eq0[keep]) and np.array_equal(et[keep], et0[keep])
+        queries = [q, q[:300], datasets.mutate(q, 0.6, rng, sm)[:450], q[100:]]
+        rc, S, EQ, ET, _ = h.search_batch(queries, 11, 1, sm.flat(), 23, 1, "SW", in_flight=3)
+        assert rc == 0
+        for k, x in enumerate(queries):
+            rc, s, eq, et, _ = h.search(x, 11, 1, sm.flat(), 23, 1, "SW")
+            assert rc == 0
+            assert np.array_equal(S[k], s) and np.array_equal(EQ[k], eq) and np.array_equal(ET[k], et)
+    finally:
+        h.close()
