@@ -488,14 +488,16 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
     return found;
 }
 
-// One thread per entry of the paired stream (pads included), so that a 35 000-residue target costs what 35 000
-// residues cost and not one warp's walk along it.  The first thread of a block finds the pair of the block's first
-// entry by bisection; the other threads walk forward from there (a pair spans at least 33 entries, so a block of
-// 256 touches at most 8 of them).
+// Work is dealt by entries of the paired stream (pads included), so that a 35 000-residue target costs what 35 000
+// residues cost and not one warp's walk along it.  A block covers kPackEntriesPerBlock consecutive entries: its first
+// thread finds the pair of the first entry by bisection -- a chain of dependent loads that costs more than everything
+// else a block of 256 entries would do, hence the larger blocks (61 -> 20 us for the 4.4 M entries of BASELINE
+// configs[1]) -- and every thread walks forward from there, entry by entry in steps of the block size.
+constexpr int kPackEntriesPerBlock = 4096;
 static __global__ void pack_pairs_kernel(const uint8_t* residues, const long long* offsets, const int* lengths, int numTargets,
                                   const long long* pairOffsets, int numPairs, long long entries, uint16_t* pairStream, int* maxCode) {
     __shared__ int basePair, blockMax;
-    const long long e0 = (long long)blockIdx.x * blockDim.x;
+    const long long e0 = (long long)blockIdx.x * kPackEntriesPerBlock;
     if (threadIdx.x == 0) {
         blockMax = 0;
         int lo = 0, hi = numPairs;  // last pair whose first column is at or before e0 (entries before pair 0 are padding)
@@ -506,20 +508,24 @@ static __global__ void pack_pairs_kernel(const uint8_t* residues, const long lon
         basePair = lo;
     }
     __syncthreads();
-    const long long e = e0 + threadIdx.x;
-    uint32_t word = 0;
-    if (e < entries && numPairs > 0) {
-        int p = basePair;
-        while (p + 1 < numPairs && pairOffsets[p + 1] <= e) p++;
-        const long long c = e - pairOffsets[p];
-        const int a = 2 * p, b = 2 * p + 1;
-        if (c >= 0 && c < lengths[a]) {
-            word = (uint32_t)residues[offsets[a] + c] + 1u;
-            if (b < numTargets && c < lengths[b]) word |= ((uint32_t)residues[offsets[b] + c] + 1u) << 8;
+    int p = basePair;
+    uint32_t mx = 0;
+    for (int it = 0; it < kPackEntriesPerBlock / 256; it++) {
+        const long long e = e0 + it * 256 + threadIdx.x;
+        if (e >= entries) break;
+        uint32_t word = 0;
+        if (numPairs > 0) {
+            while (p + 1 < numPairs && pairOffsets[p + 1] <= e) p++;
+            const long long c = e - pairOffsets[p];
+            const int a = 2 * p, b = 2 * p + 1;
+            if (c >= 0 && c < lengths[a]) {
+                word = (uint32_t)residues[offsets[a] + c] + 1u;
+                if (b < numTargets && c < lengths[b]) word |= ((uint32_t)residues[offsets[b] + c] + 1u) << 8;
+            }
         }
+        pairStream[e] = (uint16_t)word;
+        mx = max(mx, max(word & 0xffu, word >> 8));
     }
-    if (e < entries) pairStream[e] = (uint16_t)word;
-    uint32_t mx = max(word & 0xffu, word >> 8);
     mx = __reduce_max_sync(0xffffffffu, mx);
     if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&blockMax, (int)mx);
     __syncthreads();
@@ -529,13 +535,16 @@ static __global__ void pack_pairs_kernel(const uint8_t* residues, const long lon
 
 // Folded stream of the longest targets (see SearchParams::folded): entry c of target p, c in [0, T + 32), is
 // (res[c] + 1) | (res[c - 32] + 1) << 8 with 0 where the index falls outside the target; 32 zero entries before
-// the first target and after every target.  One thread per entry; at most kFoldTargets targets, found by a walk.
+// the first target and after every target.  One thread per entry; its target (one of at most kFoldTargets) by bisection.
 static __global__ void pack_folded_kernel(const uint8_t* residues, const long long* offsets, const int* lengths, const long long* foldOffsets,
                                           int numFold, long long entries, uint16_t* foldStream) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= entries) return;
-    int p = 0;
-    while (p + 1 < numFold && foldOffsets[p + 1] <= e) p++;
+    int p = 0, hi = numFold;  // last target whose first column is at or before e
+    while (hi - p > 1) {
+        const int mid = (p + hi) >> 1;
+        if (foldOffsets[mid] <= e) p = mid; else hi = mid;
+    }
     const long long c = e - foldOffsets[p];
     const int T = lengths[p];
     uint32_t word = 0;
@@ -760,7 +769,7 @@ DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed,
         if (!device_alloc(device, (void**)&d->dPairStream_, sizeof(uint16_t) * (size_t)entries)) return false;
         if (!pinned_alloc((void**)&d->hMaxCode_, sizeof(int))) return false;
         {
-            const long long blocks = (entries + 255) / 256;
+            const long long blocks = (entries + kPackEntriesPerBlock - 1) / kPackEntriesPerBlock;
             pack_pairs_kernel<<<(unsigned)blocks, 256, 0, d->stream_>>>(d->dResidues_, d->dOffsets_, d->dLengths_, n, d->dPairOffsets_,
                                                                         d->numPairs_, entries, d->dPairStream_, d->dMaxCode_);
             CUDA_TRY(cudaGetLastError());
