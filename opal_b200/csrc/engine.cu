@@ -411,13 +411,45 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
     bool found = false;
     const double tasks = (double)(hi - lo);
     const double maxLen = hi > lo ? tl.len[lo] : 0;
+    // The (strip height, group size) pairs worth pricing depend only on the query and the alphabet, not on the task
+    // range: they are filtered once and remembered (a plan prices some ninety task ranges, on the path of every
+    // drop-in call).
+    struct Viable { int Q = -1, A = 0, lanes = 0, smemLimit = 0, minPasses = 0; std::vector<std::pair<int, int>> list; };
+    static thread_local Viable memo[3];
+    Viable& viable = memo[latencyClass ? (folded ? 2 : 1) : 0];
     int minPasses = 1 << 20;  // fewest passes any geometry that fits shared memory needs
-    for (size_t ti = 0; ti < tables.size(); ti++)
-        for (int G = latencyClass ? 32 : 1; G <= 32; G *= 2) {
-            const int rows = (folded ? 2 : 1) * G * tables[ti].R;
-            const size_t smem = (size_t)planes * (A + 1) * ((G * rpad_of(tables[ti].R) + 31) / 32 * 32) * 4;
-            if (smem <= (size_t)smemLimit) minPasses = std::min(minPasses, (Q + rows - 1) / rows);
-        }
+    if (viable.Q == Q && viable.A == A && viable.lanes == lanes && viable.smemLimit == smemLimit) {
+        minPasses = viable.minPasses;
+    } else {
+        for (size_t ti = 0; ti < tables.size(); ti++)
+            for (int G = latencyClass ? 32 : 1; G <= 32; G *= 2) {
+                const int rows = (folded ? 2 : 1) * G * tables[ti].R;
+                const size_t smem = (size_t)planes * (A + 1) * ((G * rpad_of(tables[ti].R) + 31) / 32 * 32) * 4;
+                if (smem <= (size_t)smemLimit) minPasses = std::min(minPasses, (Q + rows - 1) / rows);
+            }
+        viable.Q = -1;  // list rebuilt below
+    }
+    auto worth_pricing = [&](size_t ti, int G) -> bool {
+        const int R = tables[ti].R;
+        const size_t smem = (size_t)planes * (A + 1) * ((G * rpad_of(R) + 31) / 32 * 32) * 4;
+        if (smem > (size_t)smemLimit) return false;
+        const int rows = (folded ? 2 : 1) * G * R;
+        const int passes = (Q + rows - 1) / rows;
+        if (folded && passes > 1) return false;
+        // more than a third of the swept rows padding: never the best choice unless nothing smaller exists
+        if ((long long)passes * rows * 3 > (long long)Q * 4 + 96 && !(G == (latencyClass ? 32 : 1) && ti == 0)) return false;
+        // more passes than the tallest geometry needs (one more for queries that take several anyway): the same
+        // cells plus boundary rows through HBM and further launches
+        if (passes > minPasses + (minPasses > 1 ? 1 + minPasses / 2 : 0)) return false;
+        return true;
+    };
+    if (viable.Q != Q) {
+        viable.list.clear();
+        for (size_t ti = 0; ti < tables.size(); ti++)
+            for (int G = latencyClass ? 32 : 1; G <= 32; G *= 2)
+                if (worth_pricing(ti, G)) viable.list.push_back({(int)ti, G});
+        viable.Q = Q; viable.A = A; viable.lanes = lanes; viable.smemLimit = smemLimit; viable.minPasses = minPasses;
+    }
     auto consider = [&](size_t ti, int G, int k, bool forced) {
         const int R = tables[ti].R;
         if (!latencyClass && ((t_forceK > 0 && k != t_forceK) || (t_forceG > 0 && G != t_forceG) || (t_forceR > 0 && R != t_forceR))) return;
@@ -428,12 +460,7 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
         const int rows = (folded ? 2 : 1) * G * R;  // a folded task has its second 32 R rows in the high half-words
         const int passes = (Q + rows - 1) / rows;
         if (folded && passes > 1) return;
-        // more than a third of the swept rows padding: never the best choice unless nothing smaller exists (the
-        // planner runs on the path of every drop-in call, so hopeless candidates are dropped before they are priced)
-        if (!forced && (long long)passes * rows * 3 > (long long)Q * 4 + 96 && !(G == (latencyClass ? 32 : 1) && ti == 0)) return;
-        // more passes than the tallest geometry needs (one more for queries that take several anyway): the same
-        // cells plus boundary rows through HBM and further launches
-        if (!forced && passes > minPasses + (minPasses > 1 ? 1 + minPasses / 2 : 0)) return;
+        (void)forced;
         const int groupsPerWarp = 32 / G;
         if (lo % groupsPerWarp) return;  // a warp takes groupsPerWarp consecutive tasks (and TaskLens::strided wants it so)
         // a warp-task lasts as long as its longest group: every groupsPerWarp-th task of the sorted list
@@ -472,9 +499,9 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
             out->folded = folded;
         }
     };
-    for (size_t ti = 0; ti < tables.size(); ti++)
-        for (int G = latencyClass ? 32 : 1; G <= 32; G *= 2)
-            for (int k = 1; k <= (latencyClass ? 1 : max_warps_per_partition(mode, tables[ti].R, lanes)); k++) consider(ti, G, k, false);
+    for (const auto& tg : viable.list)
+        for (int k = 1; k <= (latencyClass ? 1 : max_warps_per_partition(mode, tables[tg.first].R, lanes)); k++)
+            consider((size_t)tg.first, tg.second, k, false);
     // Development override: OPAL_B200_GEOMETRY="G,R,k" forces a geometry (ignored when it does not fit).
     if (const char* env = getenv("OPAL_B200_GEOMETRY")) {
         int G = 0, R = 0, k = 0;
