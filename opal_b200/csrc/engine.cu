@@ -386,10 +386,13 @@ static double step_cycles_lockstep(int flavorClass, int k, int R) {
     return t[6] * R / kStepR[6];
 }
 // The table was taken with all warps of a partition in lockstep (equal tasks started together), the worst case for
-// pipe contention; with tasks of mixed lengths the same probe measures 7 / 5 / 1.5 % less for k = 1 / 2 / 3.
-static const double kStepMixed[3] = {0.93, 0.95, 0.985};
+// pipe contention; with tasks of mixed lengths the same probe measures less, by a ratio that depends on the strip
+// height (SW score + end at R = 9 / 17 / 33: k = 1: 0.92 / 0.90 / 0.91, k = 2: 0.97 / 0.92 / 0.97, k = 3: 0.98 throughout).
 static double step_cycles(int flavorClass, int k, int R) {
-    return kStepMixed[std::min(std::max(k, 1), 3) - 1] * step_cycles_lockstep(flavorClass, k, R);
+    static const double ratio[3][3] = {{0.917, 0.904, 0.908}, {0.966, 0.923, 0.965}, {0.975, 0.980, 0.983}};
+    const double* r = ratio[std::min(std::max(k, 1), 3) - 1];
+    const double f = R <= 9 ? r[0] : R <= 17 ? r[0] + (r[1] - r[0]) * (R - 9) / 8.0 : R <= 33 ? r[1] + (r[2] - r[1]) * (R - 17) / 16.0 : r[2];
+    return f * step_cycles_lockstep(flavorClass, k, R);
 }
 // Resident warps per scheduler partition the kernels are compiled for (launch_bound_for in search_kernel.cuh).
 // (The 32-bit NW/HW/OV kernels at the tallest strips exist only uncapped, for two.)
