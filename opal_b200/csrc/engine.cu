@@ -463,6 +463,7 @@ static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo
         const int rows = (folded ? 2 : 1) * G * R;  // a folded task has its second 32 R rows in the high half-words
         const int passes = (Q + rows - 1) / rows;
         if (folded && passes > 1) return;
+        if (folded && mode != kModeSW && !single_event_compare(R)) return;  // tall NW / HW / OV strips are compiled without folding
         (void)forced;
         const int groupsPerWarp = 32 / G;
         if (lo % groupsPerWarp) return;  // a warp takes groupsPerWarp consecutive tasks (and TaskLens::strided wants it so)
@@ -920,12 +921,12 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
     size_t bestM = 0;
     int bestSm = 0;
     Geometry bestL, bestB;
-    // Folded variant of the latency class (SW at 16 bits): the 2 m longest TARGETS, one per warp in both half-words,
+    // Folded variant of the latency class (16 bits, one pass): the 2 m longest TARGETS, one per warp in both half-words,
     // which halves the rows per thread and with them the time of the longest target.  Needs the folded stream
     // (built for the numFold_ longest targets) and every one of those targets wanted.
     TaskLens tlFold;
     size_t foldable = 0;
-    if (lanes == 2 && mode == kModeSW && numFold_ > 0 && !getenv("OPAL_B200_NO_FOLD")) {
+    if (lanes == 2 && numFold_ > 0 && !getenv("OPAL_B200_NO_FOLD") && (mode == kModeSW || !getenv("OPAL_B200_NO_FOLD_GLOBAL"))) {
         while (foldable < (size_t)numFold_ && foldable < list.size() && list[foldable] == (int)foldable) foldable++;
         tlFold.len.assign(sortedLen_.begin(), sortedLen_.begin() + foldable);
         tlFold.build();

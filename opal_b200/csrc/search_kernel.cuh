@@ -45,6 +45,11 @@ namespace opalb200 {
 // 25 %) and capped for three (+10 % throughput over two uncapped).
 constexpr int launch_bound_for(int flavor, int R) { return (flavor == 2 && R > 24) ? 256 : 384; }
 constexpr int kModeNW = 0, kModeHW = 1, kModeOV = 2, kModeSW = 3;
+// NW / HW / OV sweeps handle their rare per-column events (result cell, last-column scan, start of the high half-words
+// of a folded task) behind ONE compare per step against the nearest event.  Measured on B200 this form is 13 % faster
+// than separate compares for strips up to 24 rows and 6 - 7 % SLOWER for taller ones (register allocation at the
+// 170-register cap), so the tall strips keep the separate compares -- and do not take folded NW / HW / OV tasks.
+__host__ __device__ constexpr bool single_event_compare(int R) { return R <= 24; }
 constexpr int kFlavorSWScore = 0, kFlavorSWEnd = 1, kFlavorGlobal = 2, kFlavorSWEndFast = 3;
 constexpr int kRowBits = 6;  // kFlavorSWEndFast: low bits of the tracked key hold 63 - row (latch_key_s16x2 spells the mask out)
 static_assert(kRowBits == 6, "latch_key_s16x2 saturates the row bits with 0x003f003f");
@@ -90,7 +95,7 @@ struct SearchParams {
     int one;            // the constant 1, opaque to the compiler (see vimax_track_s16x2)
     int keyScale;       // 1 << kRowBits, opaque to the compiler so that the key is built by an IMAD (FMA pipe)
     int fastEndLimit;   // kFlavorSWEndFast: tracked scores at or above this are re-run by the exact flavor
-    // Folded tasks (SW, Packed16, G = 32, one pass): ONE target occupies both half-words.  The low halves of the
+    // Folded tasks (Packed16, G = 32, one pass): ONE target occupies both half-words.  The low halves of the
     // warp hold query rows [0, 32 R), the high halves rows [32 R, 64 R) of the SAME target 32 columns behind, so
     // the warp is a 64-deep wavefront: what leaves the low half of thread 31 enters the high half of thread 0 one
     // step later.  Half the rows per thread means a much shorter step -- this is how the longest targets of a
@@ -417,20 +422,47 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             if (!firstPass && t == 0 && Tmax > 0) { nextBH = bH[0]; nextBF = bF[0]; }
         };
         unsigned storeLimit = (!lastPass && t == G - 1) ? (unsigned)Tmax : 0u;  // columns whose bottom row is parked
-        // OV: column of the shorter member's last-column scan inside the sweep (see below), -2 = none
+        // Rare events of a NW / HW / OV sweep, each at the END of one column of this thread (-2 = never):
+        //   OV: last-column scan of the pair's shorter member (see below; folded: of the low half-words, whose last
+        //       column is overwritten by idle columns before the sweep ends);
+        //   NW: the column(s) whose cell in the last query row is the result; only the thread that holds that row looks;
+        //   folded: column 31, after which the high half-words -- idle so far -- are set to their column -1.
+        // The sweep tests ONE column per step, the nearest event still ahead (kept opaque so that the test stays one
+        // integer-pipe compare instead of being re-derived from pass, thread, mode and lengths).
+        constexpr bool kOneCompare = single_event_compare(R);
+        const bool foldedGlobal = kOneCompare && folded && FLAVOR == kFlavorGlobal;
         int ovScanCol = (FLAVOR == kFlavorGlobal && mode == kModeOV && LANES == 2 && T[1] != T[0]) ? T[1] - 1 : -2;
-        // NW: column(s) whose cell in the last query row is the result; only the thread that holds that row looks
+        const int ovScanLane = foldedGlobal ? 0 : 1;
         int nwCol[2] = {-2, -2};
-        if (FLAVOR == kFlavorGlobal && mode == kModeNW && lastPass && t == tLast) { nwCol[0] = T[0] - 1; nwCol[1] = T[1] - 1; }
-        // kept opaque so that each test stays ONE integer-pipe compare per step instead of being re-derived from
-        // its ingredients (pass, thread, mode, lengths) with three or four
-        asm volatile("" : "+r"(storeLimit), "+r"(ovScanCol), "+r"(nwCol[0]), "+r"(nwCol[1]));
+        int jLastTask = jLast;
+        if (FLAVOR == kFlavorGlobal && mode == kModeNW && lastPass) {
+            if (!foldedGlobal) {
+                if (t == tLast) { nwCol[0] = T[0] - 1; nwCol[1] = T[1] - 1; }
+            } else {  // the last query row sits in the low or in the high half-words
+                const int pos = lastRowPadded - p.rowBase, half = pos >= foldRows ? 1 : 0, posIn = pos - half * foldRows;
+                jLastTask = posIn % R;
+                if (t == posIn / R) nwCol[half] = T[0] - 1 + half * kFoldLag;
+            }
+        }
+        if (foldedGlobal && mode == kModeOV) ovScanCol = T[0] - 1;
+        const int foldInitCol = foldedGlobal ? kFoldLag - 1 : -2;
+        auto next_event = [&](int after) {
+            int e = 0x7fffffff;
+            if (ovScanCol > after) e = min(e, ovScanCol);
+            if (nwCol[0] > after) e = min(e, nwCol[0]);
+            if (nwCol[1] > after) e = min(e, nwCol[1]);
+            if (foldInitCol > after) e = min(e, foldInitCol);
+            return e == 0x7fffffff ? -2 : e;
+        };
+        int nextEvent = next_event(-1);
+        if (kOneCompare) asm volatile("" : "+r"(storeLimit), "+r"(nextEvent));
+        else asm volatile("" : "+r"(storeLimit), "+r"(ovScanCol), "+r"(nwCol[0]), "+r"(nwCol[1]));
 
         // OV: best cell of the last target column among this thread's rows (first row on ties), half-word l
         auto scan_last_column = [&](int l) {
 #pragma unroll
             for (int j = 0; j < R; j++) {
-                const int r = myRow0 + j;
+                const int r = myRow0 + j + (l == 1 ? foldRows : 0);
                 const int v = TR::lane(HG[j], l) + Go;
                 if (r >= 0 && r < p.Q && v > lcScore[l]) { lcScore[l] = v; lcRow[l] = r; }
             }
@@ -460,7 +492,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             reg synRow = TR::splat(0), synStep = TR::splat(0);
             if (t == 0) {
                 synRow = (reg)((uint32_t)negGo & synMask);  // H = 0 in row -1 (SW, HW, OV)
-                if (!kSW && mode == kModeNW) { synRow = TR::splat(-Go - Go); synStep = negGe; }
+                if (!kSW && mode == kModeNW) { synRow = (reg)((uint32_t)TR::splat(-Go - Go) & synMask); synStep = (reg)((uint32_t)negGe & synMask); }
             }
 
 #ifdef OPAL_UNROLL2
@@ -554,8 +586,20 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                         best = latch_key_s16x2(best, bestBefore, c, colLo, colHi, keyLo, keyHi);
                 }
                 if (FLAVOR == kFlavorGlobal) {
-                    if (mode == kModeNW) {
-                        {
+                    auto track_last_row = [&]() {
+                        // last query row (HW, OV): register R-1 of thread G-1 in the last pass.  Every thread runs the
+                        // three instructions (only thread G-1's result is read), which is cheaper than branching
+                        // around them.  The shorter member of a pair needs no mask in the columns past its end: a
+                        // cell there is reached through a horizontal gap from its last real column, so it is
+                        // strictly below the value that column already contributed.
+                        // (Earlier passes run it as well; their result is never read.)
+                        bool ph, pl;
+                        best = TR::bmax(best, u, &ph, &pl);
+                        if (!pl) colLo = c;
+                        if (LANES == 2 && !ph) colHi = c;
+                    };
+                    if constexpr (!kOneCompare) {
+                        if (mode == kModeNW) {
     #pragma unroll
                             for (int l = 0; l < LANES; l++)
                                 if (c == nwCol[l]) {
@@ -564,26 +608,46 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                                     for (int j = 1; j < R; j++) if (j == jLast) v = HG[j];
                                     nwScore[l] = TR::lane(v, l) + Go;
                                 }
+                        } else {
+                            track_last_row();
+                            if (c == ovScanCol) scan_last_column(1);
                         }
                     } else {
-                        // last query row (HW, OV): register R-1 of thread G-1 in the last pass.  Every thread runs the
-                        // three instructions (only thread G-1's result is read), which is cheaper than branching
-                        // around them.  The shorter member of a pair needs no mask in the columns past its end: a
-                        // cell there is reached through a horizontal gap from its last real column, so it is
-                        // strictly below the value that column already contributed.
-                        // (Earlier passes run it as well; their result is never read.)
-                        {
-                            bool ph, pl;
-                            best = TR::bmax(best, u, &ph, &pl);
-                            if (!pl) colLo = c;
-                            if (LANES == 2 && !ph) colHi = c;
+                    if (mode != kModeNW) track_last_row();
+                    if (c == nextEvent) {  // rare: see the list of events above
+                        if (mode == kModeNW) {
+    #pragma unroll
+                            for (int l = 0; l < LANES; l++)
+                                if (c == nwCol[l]) {
+                                    reg v = HG[0];
+    #pragma unroll
+                                    for (int j = 1; j < R; j++) if (j == jLastTask) v = HG[j];
+                                    nwScore[l] = TR::lane(v, l) + Go;
+                                }
                         }
                         // last target column (OV): every real row of this thread.  Only the shorter member of a
                         // pair of unequal lengths is scanned here, where each thread meets that column at a step
                         // of its own (one active thread per scan); the longer member -- and the shorter one when
                         // the lengths are equal, the usual case in a large sorted database -- is still sitting in
                         // HG[] when the sweep ends and is scanned there by all threads at once.
-                        if (c == ovScanCol) scan_last_column(1);
+                        if (c == ovScanCol) scan_last_column(ovScanLane);
+                        if constexpr (LANES == 2) {
+                            if (c == foldInitCol) {
+                                // The high half-words have swept 32 idle columns (whatever they tracked is dropped);
+                                // their real column 0 is next: column -1 of rows 32 R ... (reference src/opal.cpp:671-679).
+                                const uint32_t lo = 0xffffu, hi = 0xffff0000u;
+    #pragma unroll
+                                for (int j = 0; j < R; j++) {
+                                    HG[j] = (HG[j] & lo) | ((uint32_t)TR::splat(border_h(mode, myRow0 + foldRows + j, Go, Ge) - Go) & hi);
+                                    E[j] = (E[j] & lo) | ((uint32_t)NEGV & hi);
+                                }
+                                diag = (diag & lo) | ((uint32_t)TR::splat(border_h(mode, myRow0 + foldRows - 1, Go, Ge) - Go) & hi);
+                                best = (best & lo) | ((uint32_t)TR::splat(TR::NEG) & hi);
+                                colHi = -1;
+                            }
+                        }
+                        nextEvent = next_event(c);
+                    }
                     }
                 }
                 if ((unsigned)c < storeLimit) {  // last thread of a group, every pass but the last: park the bottom row
@@ -610,11 +674,16 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                         if (l == 1) { cc -= folded ? kFoldLag : 0; rr += foldRows; }  // folded: same target, 32 columns behind, 32 R rows down
                     }
                 } else if (mode == kModeNW) {
-                    sc = nwScore[l]; cc = T[l] - 1; rr = p.Q - 1;
+                    sc = nwScore[l]; cc = (foldedGlobal ? T[0] : T[l]) - 1; rr = p.Q - 1;
                 } else {
-                    if (lastPass && t == G - 1 && T[l] > 0) { sc = TR::lane(best, l) + Go; cc = l ? colHi : colLo; rr = p.Q - 1; }
-                    if (mode == kModeOV && lcScore[l] != kScoreNone && better(lcScore[l], T[l] - 1, lcRow[l], sc, cc, rr)) {
-                        sc = lcScore[l]; cc = T[l] - 1; rr = lcRow[l];
+                    // last query row: the last register of the last thread (folded: of its high half-word, whose
+                    // columns are 32 behind)
+                    const int Tl = foldedGlobal ? T[0] : T[l];
+                    if (lastPass && t == G - 1 && Tl > 0 && (!foldedGlobal || l == 1)) {
+                        sc = TR::lane(best, l) + Go; cc = (l ? colHi : colLo) - (foldedGlobal ? kFoldLag : 0); rr = p.Q - 1;
+                    }
+                    if (mode == kModeOV && lcScore[l] != kScoreNone && better(lcScore[l], Tl - 1, lcRow[l], sc, cc, rr)) {
+                        sc = lcScore[l]; cc = Tl - 1; rr = lcRow[l];
                     }
                 }
                 for (int o = 1; o < G; o <<= 1) {
@@ -648,8 +717,9 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             sweep(std::integral_constant<int, FLAVOR>());
             if (FLAVOR == kFlavorGlobal && mode == kModeOV) {
                 // threads stop updating their rows after the last column of the longer member: it is still in HG[]
-                if (T[0] > 0) scan_last_column(0);
-                if (LANES == 2 && T[1] == T[0] && T[1] > 0) scan_last_column(1);
+                // (folded: only the high half-words; the low ones were scanned inside the sweep)
+                if (T[0] > 0 && !foldedGlobal) scan_last_column(0);
+                if (LANES == 2 && (foldedGlobal ? T[0] > 0 : (T[1] == T[0] && T[1] > 0))) scan_last_column(1);
             }
             reduce(false);
         }

@@ -33,20 +33,20 @@ def _tailed_db(rng, sm, n_short, n_long, long_lo, long_hi, planted=None, planted
     return SequenceDB.from_sequences([allseqs[i] for i in order])
 
 
-def _check(product, oracle, q, db, go, ge, m, alen, st, expect_folded=True):
+def _check(product, oracle, q, db, go, ge, m, alen, st, expect_folded=True, mode="SW"):
     h = product.create_db(db, 0)
     try:
-        rc, s, eq, et, _ = h.search(q, go, ge, m, alen, st, "SW")
+        rc, s, eq, et, _ = h.search(q, go, ge, m, alen, st, mode)
         assert rc == 0, product.last_error()
         folded = h.last_stats()["folded"]
         if expect_folded:
             assert folded > 0, "planner did not fold the tail of this database"
-        rc, want = search_dump(oracle, q, db, go, ge, m, alen, st, MODES["SW"])
+        rc, want = search_dump(oracle, q, db, go, ge, m, alen, st, MODES[mode])
         assert rc == 0
         assert [int(x) for x in s] == [w[1] for w in want]
         if st:
-            weq = [w[2] if w[1] > 0 else -1 for w in want]
-            wet = [w[3] if w[1] > 0 else -1 for w in want]
+            weq = [w[2] if (w[1] > 0 or mode != "SW") else -1 for w in want]
+            wet = [w[3] if (w[1] > 0 or mode != "SW") else -1 for w in want]
             assert [int(x) for x in eq] == weq
             assert [int(x) for x in et] == wet
         return folded, (s.copy(), eq.copy(), et.copy())
@@ -127,3 +127,38 @@ def test_folded_with_skipped_targets_and_batches(product, oracle):
             assert np.array_equal(S[k], s) and np.array_equal(EQ[k], eq) and np.array_equal(ET[k], et)
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("mode", ["NW", "HW", "OV"])
+@pytest.mark.parametrize("qlen", [300, 513, 700])
+def test_folded_global_modes_match_oracle(product, oracle, mode, qlen):
+    """NW / HW / OV: the high half-words of a folded task idle for 32 columns and are then set to their column -1;
+    the last query row (HW, OV), the last target column (OV: low half-words scanned inside the sweep, high ones after
+    it) and NW's final cell (in whichever half holds query row Q - 1) are picked up from the right half."""
+    rng = np.random.default_rng(300 + qlen)
+    sm = matrices.blosum62()
+    q = sm.encode(datasets.P18080)[:qlen] if qlen <= 513 else datasets.random_residues(qlen, rng, sm)
+    db = _tailed_db(rng, sm, 3000, 70, 1500, 3500, planted=q, planted_long=q)
+    for st in (0, 1):
+        folded, got = _check(product, oracle, q, db, 11, 1, sm.flat(), 23, st, mode=mode)
+    os.environ["OPAL_B200_NO_FOLD"] = "1"
+    try:
+        folded2, got2 = _check(product, oracle, q, db, 11, 1, sm.flat(), 23, 1, expect_folded=False, mode=mode)
+    finally:
+        del os.environ["OPAL_B200_NO_FOLD"]
+    assert folded2 == 0
+    for a, b in zip(got, got2):
+        assert np.array_equal(a, b)
+
+
+def test_folded_global_modes_ties_and_short_query(product, oracle):
+    """Alphabet 4 (ties everywhere) with a query that fits the low half-words alone (NW's last row then sits there)."""
+    rng = np.random.default_rng(12)
+    sm = matrices.simple(4, 2, -3)
+    seqs = [rng.integers(0, 4, int(x)).astype(np.uint8) for x in rng.integers(20, 300, 3000)]
+    seqs += [rng.integers(0, 4, int(x)).astype(np.uint8) for x in rng.integers(1500, 3000, 66)]
+    db = SequenceDB.from_sequences(seqs)
+    for qlen in (250, 330):
+        q = rng.integers(0, 4, qlen).astype(np.uint8)
+        for mode in ("NW", "HW", "OV"):
+            _check(product, oracle, q, db, 5, 2, sm.flat(), 4, 1, expect_folded=False, mode=mode)
