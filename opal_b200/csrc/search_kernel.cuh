@@ -10,8 +10,9 @@
 //     row), so a group covers G*R query rows per pass; longer queries take several passes with
 //     the boundary row (H, F per target column) parked in HBM between passes;
 //   * at step s thread t computes target column s - t; the bottom (H, F) of its strip travels
-//     to thread t+1 with one __shfl_up_sync per value, so no DP state ever leaves registers
-//     within a pass;
+//     to thread t+1 with one rotating __shfl_sync per value, so no DP state ever leaves registers
+//     within a pass (the rotation also serves the folded sweep, SearchParams::folded, in which one
+//     target fills both 16-bit lanes of a warp and thread 31's low lane feeds thread 0's high lane);
 //   * the two 16-bit halves of every register hold two DIFFERENT targets (Rognes/Opal style), and
 //     the recurrence is issued as packed DPX instructions: VIADDMNMX.S16x2 (E, F, diagonal+max),
 //     VIMNMX.S16x2, VIADD.16x2;  the 32-bit re-run uses the s32 forms of the same instructions;
