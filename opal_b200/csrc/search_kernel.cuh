@@ -48,9 +48,10 @@ constexpr int launch_bound_for(int flavor, int R) { return (flavor == 2 && R > 2
 constexpr int kModeNW = 0, kModeHW = 1, kModeOV = 2, kModeSW = 3;
 // NW / HW / OV sweeps handle their rare per-column events (result cell, last-column scan, start of the high half-words
 // of a folded task) behind ONE compare per step against the nearest event.  Measured on B200 this form is 13 % faster
-// than separate compares for strips up to 24 rows and 6 - 7 % SLOWER for taller ones (register allocation at the
-// 170-register cap), so the tall strips keep the separate compares -- and do not take folded NW / HW / OV tasks.
-__host__ __device__ constexpr bool single_event_compare(int R) { return R <= 24; }
+// than separate compares at 18 rows and 3 - 7 % SLOWER at 24 - 33 (the event block inflates the loop; register
+// allocation at the 170-register cap), so the tall strips keep the separate compares -- and do not take folded
+// NW / HW / OV tasks.
+__host__ __device__ constexpr bool single_event_compare(int R) { return R <= 18; }
 constexpr int kFlavorSWScore = 0, kFlavorSWEnd = 1, kFlavorGlobal = 2, kFlavorSWEndFast = 3;
 constexpr int kRowBits = 6;  // kFlavorSWEndFast: low bits of the tracked key hold 63 - row (latch_key_s16x2 spells the mask out)
 static_assert(kRowBits == 6, "latch_key_s16x2 saturates the row bits with 0x003f003f");
