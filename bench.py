@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- GCUPS of the database-search hot path on N B200s, beside the reference on host cores.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload config2|config3]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload config3|config2]
 
-A step is one pass of the hot path: one query against one resident database (per GPU).  The
-default workload is BASELINE.json configs[1]: SW score+end, query P18080 (513 aa) against a
-synthetic 12,071-sequence Swiss-Prot-length-distributed database, BLOSUM62, gaps 11/1.  With
-N > 1 (one process per GPU under torchrun) every rank holds its own 12,071-sequence shard of an
-N x 12,071-sequence database (weak scaling, no data-path collective: targets are independent).
-`--workload config3` runs the 570k-sequence / 206 M-residue database of configs[2] instead,
-dealt residue-balanced over the ranks (strong scaling).
+Default workload = BASELINE.json configs[2], the largest single-GPU configuration: the 20 customary query
+lengths 144 ... 5478 in the modes NW, HW and OV (score + end location) against the synthetic 570k-sequence /
+207 M-residue Swiss-Prot-shaped database, BLOSUM62, gaps 11/1 -- the reference's own performance protocol, modes x
+queries over one big database (reference test/perf:15-24), timed like the reference times it (the search call only,
+src/opal_aligner.cpp:157-165) and scored with its formula, GCUPS = queryLength * sum(dbSeqLengths) / 1e9 / seconds
+(src/opal_aligner.cpp:205-206).  A STEP is one sweep of that set: 60 searches, 25.9 T cell updates.  With N > 1 (one
+process per GPU under torchrun) the database is dealt residue-balanced over the ranks (STRONG scaling; targets are
+independent, so there is no data-path collective) and every rank runs the same 60 searches against its shard.
 
-Metric: GCUPS = queryLength * sum(dbSeqLengths) / 1e9 / seconds (reference
-src/opal_aligner.cpp:205-206).  `value` is device-timed (CUDA events on the library's stream, first
-kernel launch to last kernel end, database resident, max over ranks); `e2e` goes through the
-reference-facing C ABI call opalSearchDatabase with host buffers, so database packing, H2D, D2H
-and the per-record result writes are all inside its timed region.
+  value  device-timed: CUDA events on the library's streams, start of a batch of queries to its last kernel end,
+         database resident in HBM, summed over the steps, max over ranks.
+  e2e    the same sweep through the reference-facing C ABI call opalSearchDatabase, one call per (query, mode) with
+         HOST buffers: database packing, H2D, kernels, D2H and the per-record result writes are all inside its
+         timed region, every call.
+
+`--workload config2` is BASELINE configs[1] (SW score+end, P18080 vs 12,071 sequences; weak scaling, one shard of
+equal work per GPU) -- the headline of round 1, kept as a secondary measurement.
+`--shard-of M` (development) runs rank 0's shard of an M-way deal on one GPU: the per-GPU time of an M-GPU run.
 """
 import argparse
 import json
@@ -29,33 +34,54 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from opal_b200 import (MODES, OPAL_OVERFLOW_BUCKETS, OPAL_SEARCH_SCORE_END, OpalCLibrary, SequenceDB,  # noqa: E402
-                       datasets, matrices, new_results, sharding)
+from opal_b200 import (MODES, OPAL_OVERFLOW_BUCKETS, OPAL_SEARCH_SCORE, OPAL_SEARCH_SCORE_END, OpalCLibrary,  # noqa: E402
+                       SequenceDB, datasets, matrices, new_results, sharding)
 
 GAP_OPEN, GAP_EXT = 11, 1
-MODE = "SW"
+CPU_MAX_TARGET = 20000  # the reference's NW/HW/OV 32-bit pass is undefined behaviour: keep it out of the CPU sample
 
 
 # ----------------------------------------------------------------------------- workloads
-def make_workload(name, rank, world):
-    sm = matrices.blosum62()
-    query = sm.encode(datasets.P18080)
+class Workload:
+    pass
+
+
+def make_workload(name, rank, world, shard_of=0):
+    w = Workload()
+    w.name, w.sm = name, matrices.blosum62()
+    sm = w.sm
+    p18080 = sm.encode(datasets.P18080)
     if name == "config2":
         # weak scaling: every GPU gets a shard of exactly the same work -- the same lengths and planted homologs, the
         # background residues redrawn per rank -- so that the per-GPU tail (the longest target) does not vary by rank
-        db = datasets.config2_db(sm, query, residue_seed=None if rank == 0 else 20261017 + rank)
-        desc = ("BASELINE configs[1]: SW score+end, P18080 (Q=513) vs synthetic 12,071-seq Swiss-Prot-shaped DB, "
-                "BLOSUM62 11/1; one such shard per GPU (same lengths, residues redrawn per rank)")
-        scaling = "weak"
+        w.db = datasets.config2_db(sm, p18080, residue_seed=None if rank == 0 else 20261017 + rank)
+        w.full_sequences, w.full_residues = len(w.db) * world, None
+        w.queries, w.modes, w.search_type = [p18080], ["SW"], OPAL_SEARCH_SCORE_END
+        w.desc = ("BASELINE configs[1]: SW score+end, P18080 (Q=513) vs synthetic 12,071-seq Swiss-Prot-shaped DB, "
+                  "BLOSUM62 11/1; one such shard per GPU (same lengths, residues redrawn per rank)")
+        w.scaling = "weak"
     elif name == "config3":
-        full = datasets.config3_db(sm, query=query)
-        db = sharding.shard_db(full, sharding.deal_shards(full.lengths, world)[rank]) if world > 1 else full
-        desc = ("BASELINE configs[2] DB: 570k seqs / ~206M residues, Swiss-Prot-shaped with heavy tail, "
-                "SW score+end, P18080 (Q=513), BLOSUM62 11/1; DB dealt residue-balanced over the GPUs")
-        scaling = "strong"
+        full = datasets.config3_db(sm, query=p18080)
+        w.full_sequences, w.full_residues = len(full), full.total_residues
+        parts = shard_of if shard_of > 1 else world
+        w.db = sharding.shard_db(full, sharding.deal_shards(full.lengths, parts)[rank if shard_of <= 1 else 0]) if parts > 1 else full
+        w.full_db = full
+        w.queries = sorted(datasets.config3_queries(sm), key=len, reverse=True)  # longest first: the batch ends on short tails
+        w.modes, w.search_type = ["NW", "HW", "OV"], OPAL_SEARCH_SCORE_END
+        w.desc = ("BASELINE configs[2]: NW/HW/OV score+end, the 20 query lengths 144..5478 (sum 41,752) vs synthetic "
+                  "570k-seq / 207M-residue Swiss-Prot-shaped DB with a heavy tail up to 35,213, BLOSUM62 11/1; one step = "
+                  "60 searches (reference test/perf protocol); DB dealt residue-balanced over the GPUs")
+        w.scaling = "strong"
     else:
         raise SystemExit(f"unknown workload {name}")
-    return sm, query, db, desc, scaling
+    w.sum_q = int(sum(len(q) for q in w.queries))
+    return w
+
+
+def config_of(w):
+    """The `config` object: identical in both arms (same workload, same keys)."""
+    return {"workload": w.desc, "modes": w.modes, "search": "score+end", "query_lengths": sorted(len(q) for q in w.queries),
+            "matrix": "BLOSUM62", "gap_open": GAP_OPEN, "gap_ext": GAP_EXT, "db_sequences": w.full_sequences}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -91,7 +117,7 @@ class ClockSampler:
     def _loop(self):
         while not self.stop_flag:
             self.sample()
-            time.sleep(0.005)
+            time.sleep(0.02)
 
     def start(self):
         self.thread = threading.Thread(target=self._loop, daemon=True)
@@ -106,26 +132,6 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def ncu_dram_bytes_per_launch():
-    """DRAM bytes of the dominant kernel launch from the committed ncu capture (None if it is not there)."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_search_kernel.txt")
-    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    best = None
-    try:
-        cur = {}
-        for line in open(path):
-            tok = line.split()
-            if len(tok) >= 3 and tok[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and tok[1] in unit:
-                cur[tok[0]] = float(tok[2].replace(",", "")) * unit[tok[1]]
-                if len(cur) == 2:
-                    total = sum(cur.values())
-                    best = total if best is None else max(best, total)
-                    cur = {}
-        return best
-    except OSError:
-        return None
-
-
 def cpu_library():
     ref = os.path.join(ROOT, "oracle", "_ref", "libopal_ref.so")
     if os.path.exists(ref):
@@ -137,15 +143,21 @@ def cpu_library():
     return OpalCLibrary(port), "port"
 
 
-def cpu_search(lib, sm, query, shards, search_type=OPAL_SEARCH_SCORE_END):
-    """One search of `query` against all shards, one host thread per shard (the reference is
-    re-entrant; ctypes releases the GIL). Returns wall seconds."""
+def cpu_sweep(lib, w, shards):
+    """One sweep (every mode x every query) against all shards, one host thread per shard (the reference is
+    re-entrant; ctypes releases the GIL).  Returns wall seconds."""
+    sm = w.sm
     results = [new_results(len(s)) for s in shards]
+    blank = [r.copy() for r in results]
     rcs = [0] * len(shards)
 
     def work(k):
-        rcs[k], _ = lib.search_database(query, shards[k], GAP_OPEN, GAP_EXT, sm.flat(), sm.alphabet_length, results[k],
-                                        search_type, MODES[MODE], OPAL_OVERFLOW_BUCKETS)
+        for mode in w.modes:
+            for q in w.queries:
+                results[k][:] = blank[k]
+                rc, _ = lib.search_database(q, shards[k], GAP_OPEN, GAP_EXT, sm.flat(), sm.alphabet_length, results[k],
+                                            w.search_type, MODES[mode], OPAL_OVERFLOW_BUCKETS)
+                rcs[k] |= rc
 
     threads = [threading.Thread(target=work, args=(k,)) for k in range(len(shards))]
     t0 = time.perf_counter()
@@ -158,35 +170,47 @@ def cpu_search(lib, sm, query, shards, search_type=OPAL_SEARCH_SCORE_END):
     return dt
 
 
-def split_for_threads(db, nthreads, stride=1):
+def split_for_threads(db, nthreads, stride=1, max_len=None):
     """Contiguous residue-balanced shards of every `stride`-th sequence of the length-sorted DB."""
-    order = np.argsort(db.lengths, kind="stable")[::stride]
+    order = np.argsort(db.lengths, kind="stable")
+    if max_len is not None:
+        order = order[db.lengths[order] <= max_len]
+    order = order[::stride]
     lens = db.lengths[order].astype(np.int64)
     bounds = np.searchsorted(np.cumsum(lens), np.linspace(0, lens.sum(), nthreads + 1)[1:-1])
     parts = np.split(order, bounds)
     return [db.subset(p) for p in parts if len(p)], int(lens.sum())
 
 
+def cpu_sample(w, db, seconds):
+    """Shards of a stratified sample of `db` sized for about `seconds` of host work per sweep (assuming ~4 GCUPS per
+    host thread, the order of what the AVX2 reference reaches in these modes)."""
+    cores = os.cpu_count() or 1
+    cells = float(w.sum_q) * len(w.modes) * db.total_residues
+    stride = max(1, int(np.ceil(cells / (seconds * 4e9 * cores))))
+    shards, residues = split_for_threads(db, cores, stride, CPU_MAX_TARGET if w.name == "config3" else None)
+    note = (f"every {stride}-th sequence of the length-sorted DB" + (f" among those <= {CPU_MAX_TARGET} residues" if w.name == "config3" else "")
+            + f" ({residues} residues), {len(w.modes) * len(w.queries)} searches per sweep, one std thread per contiguous residue-balanced shard")
+    return shards, residues, note
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    sm, query, db, desc, scaling = make_workload(args.workload, 0, 1)
+    w = make_workload(args.workload, 0, 1)
     lib, kind = cpu_library()
-    cores = os.cpu_count() or 1
-    # bounded sample: ~2 G cells per step keeps K steps within a couple of minutes on any host
-    stride = max(1, int(len(query) * db.total_residues / 2.5e9))
-    shards, residues = split_for_threads(db, cores, stride)
+    shards, residues, note = cpu_sample(w, w.db, 4.0)
     for _ in range(max(1, min(args.warmup, 2))):
-        cpu_search(lib, sm, query, shards)
-    secs = sum(cpu_search(lib, sm, query, shards) for _ in range(args.steps))
-    cells = len(query) * residues * args.steps
+        cpu_sweep(lib, w, shards)
+    secs = sum(cpu_sweep(lib, w, shards) for _ in range(args.steps))
+    cells = float(w.sum_q) * len(w.modes) * residues * args.steps
     value = cells / 1e9 / secs
-    sample = f"every {stride}-th sequence of the length-sorted DB ({residues} residues), {len(shards)} threads, per step"
     line = {"impl": "reference", "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
-            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "int8/int16 (AVX2)" if kind == "reference" else "int64",
-            "data": "synthetic", "config": {"workload": desc, "mode": MODE, "search": "score+end", "query_length": int(len(query))},
-            "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": len(shards), "kind": kind, "sample": sample},
+            "higher_is_better": True, "scaling": w.scaling, "vs_baseline": None,
+            "dtype": "int8/int16/int32 (AVX2)" if kind == "reference" else "int64",
+            "data": "synthetic", "config": config_of(w),
+            "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": len(shards), "kind": kind, "sample": note + ", per step"},
             "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -213,32 +237,39 @@ def run_b200_arm(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce(x, op):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
         return float(t.item())
 
     eng = OpalB200()
-    sm, query, db, desc, scaling = make_workload(args.workload, rank, world)
-    mat, A, Q = sm.flat(), sm.alphabet_length, int(len(query))
+    w = make_workload(args.workload, rank, world, args.shard_of)
+    sm, db = w.sm, w.db
+    mat, A = sm.flat(), sm.alphabet_length
     handle = eng.create_db(db, local_rank)
-    cells_rank = Q * db.total_residues
+    cells_rank = float(w.sum_q) * len(w.modes) * db.total_residues  # per step
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    single = len(w.queries) == 1
+    nq, n = len(w.queries), len(db)
+    out = None if single else tuple(np.zeros((nq, n), dtype=np.int32) for _ in range(3))
 
     def step_resident():
+        """One sweep against the resident database; returns (device ms, kernel launches)."""
         flush.zero_()
         torch.cuda.synchronize()
-        rc, sc, eq, et, ms = handle.search(query, GAP_OPEN, GAP_EXT, mat, A, OPAL_SEARCH_SCORE_END, MODE)
-        if rc != 0:
-            raise SystemExit(f"search failed rc={rc}: {eng.last_error()}")
-        return ms, sc
+        ms_total, launches = 0.0, 0
+        for mode in w.modes:
+            if single:
+                rc, sc, _, _, ms = handle.search(w.queries[0], GAP_OPEN, GAP_EXT, mat, A, w.search_type, mode)
+            else:
+                rc, sc, _, _, ms = handle.search_batch(w.queries, GAP_OPEN, GAP_EXT, mat, A, w.search_type, mode,
+                                                       in_flight=args.in_flight, out=out)
+            if rc != 0:
+                raise SystemExit(f"search failed rc={rc}: {eng.last_error()}")
+            ms_total += ms
+            launches += handle.last_stats()["kernel_launches"]
+        return ms_total, launches
 
     # ---- device-timed value (database resident)
     for _ in range(args.warmup):
@@ -249,129 +280,141 @@ def run_b200_arm(args, rank, local_rank, world):
     wall0 = time.perf_counter()
     dev_ms, launches = 0.0, 0
     for _ in range(args.steps):
-        ms, sc = step_resident()
+        ms, ln = step_resident()
         dev_ms += ms
-        launches += handle.last_stats()["kernel_launches"]
+        launches += ln
     barrier()
     wall_resident = time.perf_counter() - wall0
     clk = clocks.stop()
-    stats = handle.last_stats()
-    t_dev = max_over_ranks(dev_ms / 1e3)
-    total_cells = sum_over_ranks(float(cells_rank)) * args.steps
+    t_dev = reduce(dev_ms / 1e3, "MAX")
+    t_wall = reduce(wall_resident, "MAX")
+    total_cells = reduce(cells_rank, "SUM") * args.steps
     value = total_cells / 1e9 / t_dev
+    last_scores = {}
+    if not single:  # kept for the cross-check with the drop-in path below: last mode, every query
+        last_scores = {len(q): out[0][k].copy() for k, q in enumerate(w.queries)}
 
-    # ---- end to end through the drop-in C ABI (host buffers in, OpalSearchResult records out)
+    # ---- end to end through the drop-in C ABI (host buffers in, OpalSearchResult records out), one call per search
+    blank = new_results(n)
+    res = blank.copy()
+
     def step_e2e():
-        res = new_results(len(db))
-        rc, res = eng.search_database(query, db, GAP_OPEN, GAP_EXT, mat, A, res, OPAL_SEARCH_SCORE_END, MODES[MODE],
-                                      OPAL_OVERFLOW_BUCKETS)
-        if rc != 0:
-            raise SystemExit(f"opalSearchDatabase failed rc={rc}: {eng.last_error()}")
-        return res
+        for mode in w.modes:
+            for q in w.queries:
+                res[:] = blank  # the caller's opalInitSearchResult loop (reference src/opal_aligner.cpp:150-154)
+                rc, _ = eng.search_database(q, db, GAP_OPEN, GAP_EXT, mat, A, res, w.search_type, MODES[mode], OPAL_OVERFLOW_BUCKETS)
+                if rc != 0:
+                    raise SystemExit(f"opalSearchDatabase failed rc={rc}: {eng.last_error()}")
 
-    for _ in range(min(args.warmup, 3)):
-        res = step_e2e()
-    assert (res["score"] == sc).all(), "drop-in call and resident handle disagree"
+    step_e2e()
+    if last_scores:
+        assert (res["score"] == last_scores[len(w.queries[-1])]).all(), "drop-in call and resident handle disagree"
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
     barrier()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    t_e2e = reduce(time.perf_counter() - t0, "MAX")
     e2e_value = total_cells / 1e9 / t_e2e
-    # one upload block [offsets | pair offsets | fold offsets | lengths | max code | residues] + one argument block
-    # [counters | matrix | query]; the folded stream of the longest targets is built on the device (at most 128 offsets go up)
-    n_fold = max(min(len(db) & ~1, 128), 1)
-    index_bytes = (8 * (len(db) + 1) + 8 * max((len(db) + 1) // 2, 1) + 8 * n_fold + 4 * (max(len(db), 1) + 1) + 255) // 256 * 256
-    h2d = int(index_bytes + db.total_residues + 64 + 1024 + (4 * A * A + 255) // 256 * 256 + Q + 16)
-    d2h = int(3 * 4 * len(db) + 4)
+    # per call: one upload block [offsets | pair offsets | fold offsets | lengths | max code | residues] + one argument
+    # block [counters | matrix | query]; three result arrays come back
+    n_fold = max(min(n & ~1, 128), 1)
+    index_bytes = (8 * (n + 1) + 8 * max((n + 1) // 2, 1) + 8 * n_fold + 4 * (max(n, 1) + 1) + 255) // 256 * 256
+    calls = len(w.modes) * nq
+    h2d = int(calls * (index_bytes + db.total_residues + 64 + 1024 + (4 * A * A + 255) // 256 * 256 + 16) + len(w.modes) * w.sum_q)
+    d2h = int(calls * (3 * 4 * n + 4))
 
-    # ---- many queries against the resident database: same metric, several queries in flight
-    nq = 32
-    rng = np.random.default_rng(7)
-    batch = [query] + [datasets.mutate(query, 0.5, rng, sm)[:Q] for _ in range(nq - 1)] if args.workload == "config2" else \
-            [query] + [datasets.random_residues(Q, rng, sm) for _ in range(3)]
-    batch_cells = float(sum(len(x) for x in batch)) * db.total_residues
-    rc, *_ = handle.search_batch(batch, GAP_OPEN, GAP_EXT, mat, A, OPAL_SEARCH_SCORE_END, MODE, in_flight=3)
-    if rc != 0:
-        raise SystemExit(f"batch search failed rc={rc}: {eng.last_error()}")
-    barrier()
-    t0 = time.perf_counter()
-    rc, _, _, _, batch_ms = handle.search_batch(batch, GAP_OPEN, GAP_EXT, mat, A, OPAL_SEARCH_SCORE_END, MODE, in_flight=3)
-    barrier()
-    t_batch_wall = max_over_ranks(time.perf_counter() - t0)
-    t_batch_dev = max_over_ranks(batch_ms / 1e3)
-    batch_total = sum_over_ranks(batch_cells)
-    multi_query = {"queries": len(batch), "in_flight": 3, "value": batch_total / 1e9 / t_batch_dev, "unit": "GCUPS",
-                   "wall_value": batch_total / 1e9 / t_batch_wall,
-                   "note": "opalb200_db_search_batch on the resident database: device-timed (CUDA events, first launch of the "
-                           "batch to last kernel end) and wall-clock with host buffers in and out"}
+    # ---- extras (rank 0's shard, untimed region): every (mode, query) alone, score+end and score only; SW beside them
+    extras = {}
+    if rank == 0 and not single and not args.no_extras:
+        per_query = {}
+        for mode in w.modes + ["SW"]:
+            for st, key in ((OPAL_SEARCH_SCORE_END, "score+end"), (OPAL_SEARCH_SCORE, "score")):
+                row = {}
+                for q in sorted(w.queries, key=len):
+                    rc, _, _, _, ms = handle.search(q, GAP_OPEN, GAP_EXT, mat, A, st, mode)
+                    if rc != 0:
+                        raise SystemExit(f"search failed rc={rc}: {eng.last_error()}")
+                    row[str(len(q))] = round(len(q) * db.total_residues / 1e6 / ms, 1)
+                per_query[f"{mode} {key}"] = row
+        extras["per_query_gcups_one_gpu"] = {
+            "note": "single searches on rank 0's shard, device-timed first launch to last kernel end, GCUPS of one GPU by query length",
+            "table": per_query}
 
-    # ---- roofline of the dominant kernel: packed-DPX issue rate (measured live) and HBM streaming
-    peak_gcups, instr_per_s, _ = eng.measure_dpx_peak(local_rank)
+    # ---- roofline of the dominant kernel class: packed-DPX issue rate (measured live) and HBM streaming
+    global_modes = all(m != "SW" for m in w.modes)
+    peak_gcups, instr_per_s, _ = eng.measure_dpx_peak(local_rank, mix=1 if global_modes else 0)
     per_gpu = value / world
-    hbm_peak = None
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             hbm_peak = float(json.load(f)["hbm_gbs"])
         hbm_src = "measured (MEASURED_PEAKS.json)"
     except Exception:
-        hbm_peak, hbm_src = 6650.0, "fallback"
-    hbm_gbs = db.total_residues * args.steps / (dev_ms / 1e3) / 1e9
-    traffic = ncu_dram_bytes_per_launch() if args.workload == "config2" else None
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    hbm_gbs = db.total_residues * calls * args.steps / (dev_ms / 1e3) / 1e9
+    instr = 5 if global_modes else 6
     roofline = {
         "bound": "dpx (integer pipe)", "achieved": per_gpu, "peak": peak_gcups, "unit": "GCUPS", "frac": per_gpu / peak_gcups,
-        "traffic": traffic,
-        "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the dominant (bulk) search_kernel launch, from the committed "
-                        "ncu --set full capture profiles/r1_ncu_search_kernel.txt; algorithmic bytes per launch = residues of its targets",
-        "peak_source": f"measured live: {instr_per_s / 1e12:.2f} T packed s16x2 thread-instr/s x 2 cells / 6 instr (SW)",
+        "traffic": None,
+        "traffic_note": "not measurable in-run; dram__bytes of the bulk launches are in the committed ncu --set full captures "
+                        "(profiles/README.md): traffic = algorithmic bytes, DRAM < 1 % busy",
+        "achieved_note": "whole step (all launches, tails and launch gaps included) per GPU; algorithmic work = "
+                         f"{instr} packed s16x2 instructions per 2 cells ({'NW/HW/OV' if global_modes else 'SW'} recurrence, SURVEY.md 8d)",
+        "peak_source": f"measured live: {instr_per_s / 1e12:.2f} T packed s16x2 thread-instr/s x 2 cells / {instr} instr",
         "hbm": {"bound": "hbm", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
                 "peak_source": hbm_src, "note": "algorithmic bytes = 1 B per DB residue per query (1/Q B per cell)"},
     }
 
     line = None
     if rank == 0:
+        stats = handle.last_stats()
         line = {"metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-                "dtype": "s16x2 (DPX), s32 re-run on overflow", "data": "synthetic",
-                "config": {"workload": desc, "mode": MODE, "search": "score+end", "query_length": Q,
-                           "db_sequences_per_gpu": len(db), "db_residues_per_gpu": db.total_residues,
-                           "l2": "256 MiB flush buffer written between timed steps",
-                           "geometry": {k: stats[k] for k in ("G", "R", "passes", "warps_per_partition", "groups", "folded")}},
+                "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": w.scaling, "vs_baseline": None,
+                "dtype": "s16x2 (DPX), s32 where 16 bits cannot hold the scores", "data": "synthetic",
+                "config": config_of(w),
+                "details": {"db_sequences_per_gpu": n, "db_residues_per_gpu": db.total_residues,
+                            "cells_per_step": total_cells / args.steps, "queries_in_flight": 1 if single else args.in_flight,
+                            "l2": "256 MiB flush buffer written between timed steps",
+                            "wall_ms_per_step_resident": t_wall / args.steps * 1e3,
+                            "last_geometry": {k: stats[k] for k in ("G", "R", "passes", "warps_per_partition", "groups", "folded")}},
                 "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": t_e2e / args.steps * 1e3, "path": "opalSearchDatabase (pack + H2D + kernels + D2H + records)"},
-                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "multi_query": multi_query,
-                "wall_ms_per_step_resident": wall_resident / args.steps * 1e3}
+                        "ms_per_step": t_e2e / args.steps * 1e3,
+                        "path": f"opalSearchDatabase x {calls} per step (each: pack + H2D + kernels + D2H + records)"},
+                "gpu_launches": launches, "clocks": clk, "roofline": roofline}
+        if args.shard_of > 1:
+            line["details"]["emulation"] = f"rank 0's shard of a {args.shard_of}-way deal on one GPU (development run, not a scaling result)"
+        line.update(extras)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         lib, kind = cpu_library()
-        cores = os.cpu_count() or 1
-        stride = max(1, int(Q * db.total_residues / 2.5e9))
-        shards, residues = split_for_threads(db, cores, stride)
-        cpu_search(lib, sm, query, shards)
+        shards, residues, note = cpu_sample(w, w.full_db if hasattr(w, "full_db") else db, 4.0)
+        cpu_sweep(lib, w, shards)
         reps, secs = 0, 0.0
-        while secs < 10.0 and reps < 200:
-            secs += cpu_search(lib, sm, query, shards)
+        while secs < 12.0 and reps < 200:
+            secs += cpu_sweep(lib, w, shards)
             reps += 1
-        line["cpu_baseline"] = {"value": Q * residues * reps / 1e9 / secs, "unit": "GCUPS", "cores": len(shards), "kind": kind,
-                                "sample": f"every {stride}-th sequence of the length-sorted DB ({residues} residues) x {reps} "
-                                          f"searches, one std thread per contiguous residue-balanced shard"}
+        line["cpu_baseline"] = {"value": float(w.sum_q) * len(w.modes) * residues * reps / 1e9 / secs, "unit": "GCUPS",
+                                "cores": len(shards), "kind": kind, "sample": note + f", x {reps} sweeps"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     handle.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3"])
+    ap.add_argument("--workload", default="config3", choices=["config2", "config3"])
+    ap.add_argument("--in-flight", type=int, default=4, help="queries of a batch on the device at a time")
+    ap.add_argument("--shard-of", type=int, default=0, help="development: run one shard of an M-way deal on one GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

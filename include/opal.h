@@ -23,6 +23,10 @@ extern "C" {
 #define OPAL_ERR_OVERFLOW 1        /* a score does not fit the 32-bit range the library guarantees */
 #define OPAL_ERR_NO_SIMD_SUPPORT 2 /* reference: no SSE4.1/AVX2; here: no usable sm_100 device / CUDA failure */
 #define OPAL_ERR_INVALID_MODE 3    /* mode is none of NW/HW/OV/SW */
+/* Addition of this library (the reference reads out of bounds instead, src/opal.cpp:265): alphabetLength outside
+ * [1, 256], a residue code >= alphabetLength in the query or the database, a negative gap penalty.  The text is
+ * available from opalb200_last_error() (opal_b200.h). */
+#define OPAL_ERR_INVALID_ARGUMENT 4
 
 /* Alignment modes (reference src/opal.h:22-25). */
 #define OPAL_MODE_NW 0 /* global */
@@ -87,7 +91,15 @@ void opalSearchResultSetScore(OpalSearchResult* result, int score);
  * OPAL_SEARCH_ALIGNMENT its score and end are used to derive start+alignment.
  *
  * Returns 0, or OPAL_ERR_OVERFLOW / OPAL_ERR_NO_SIMD_SUPPORT /
- * OPAL_ERR_INVALID_MODE.
+ * OPAL_ERR_INVALID_MODE / OPAL_ERR_INVALID_ARGUMENT.
+ *
+ * Inputs the reference leaves undefined (src/opal.cpp:263-265, 330-331) are defined here: a zero-length target (or
+ * query) scores as an alignment against nothing -- 0 for SW and OV, the cost of one gap over the other sequence for NW
+ * (and for HW when the target is empty) -- with end location (queryLength - 1, targetLength - 1), i.e. -1 on the empty
+ * side; OPAL_SEARCH_ALIGNMENT leaves such a record without start, end and alignment (alignmentLength 0).
+ *
+ * With several GPUs (environment OPAL_B200_DEVICES=all or a comma-separated list of ordinals) one call deals the
+ * database over those devices, balanced by residue count, and searches them concurrently; the records are the same.
  */
 int opalSearchDatabase(
     unsigned char query[], int queryLength, unsigned char* db[], int dbLength,

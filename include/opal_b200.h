@@ -26,6 +26,13 @@ int opalb200_device_count(void);
 const char* opalb200_last_error(void);
 
 /*
+ * The library recycles device and pinned host allocations between calls instead of returning them to the driver
+ * (a drop-in opalSearchDatabase call would otherwise spend more time in cudaMalloc than searching): up to 8 GB of
+ * device memory per GPU and 2 GB of pinned memory may sit in that cache.  This returns all of it.
+ */
+void opalb200_trim_cache(void);
+
+/*
  * Length-sorts the database (longest first), concatenates it in that order and uploads it to
  * `device`'s HBM.  Same db / dbLength / dbSeqLengths meaning as opalSearchDatabase
  * (reference src/opal.h:107-109).  Returns NULL on failure.
@@ -112,6 +119,9 @@ int opalb200_db_last_folded(const OpalB200Db* handle);
  * thread-instructions/s and the kernel time.
  */
 double opalb200_measure_dpx_peak(int device, double* threadInstrPerSec, float* ms);
+/* Same with the instruction mix of the recurrence chosen: mix 0 = SW (6 packed instructions per 2 cells, the function
+ * above), mix 1 = NW / HW / OV (5: no running maximum per cell). */
+double opalb200_measure_dpx_peak_mix(int device, int mix, double* threadInstrPerSec, float* ms);
 
 #ifdef __cplusplus
 }

@@ -185,6 +185,11 @@ int opalb200_device_count(void) {
 
 const char* opalb200_last_error(void) { return last_error(); }
 
+void opalb200_trim_cache(void) {
+    DeviceGuard guard;
+    trim_cache();
+}
+
 OpalB200Db* opalb200_db_create(unsigned char* db[], int dbLength, const int dbSeqLengths[], int device) {
     DeviceGuard guard;
     return reinterpret_cast<OpalB200Db*>(DeviceDb::create(db, dbLength, dbSeqLengths, device));
@@ -287,7 +292,12 @@ int opalb200_db_last_folded(const OpalB200Db* h) { return reinterpret_cast<const
 
 double opalb200_measure_dpx_peak(int device, double* threadInstrPerSec, float* ms) {
     DeviceGuard guard;
-    return measure_dpx_peak(device, threadInstrPerSec, ms);
+    return measure_dpx_peak(device, 0, threadInstrPerSec, ms);
+}
+
+double opalb200_measure_dpx_peak_mix(int device, int mix, double* threadInstrPerSec, float* ms) {
+    DeviceGuard guard;
+    return measure_dpx_peak(device, mix != 0 ? 1 : 0, threadInstrPerSec, ms);
 }
 
 }  // extern "C"

@@ -85,12 +85,12 @@ struct DeviceInfo { bool known = false; int numSMs = 0, smemLimit = 0, major = 0
 struct CachedBlock { void* p; size_t bytes; };
 struct ResourceCache {
     std::mutex mu;
-    std::vector<CachedBlock> freeDevice[16], freePinned;
+    std::vector<CachedBlock> freeDevice[kMaxDevices], freePinned;
     std::unordered_map<void*, size_t> liveBytes;
-    std::vector<cudaStream_t> streams[16];
-    std::vector<cudaEvent_t> events[16];
-    DeviceInfo info[16];
-    size_t cachedDevice[16] = {0}, cachedPinned = 0;
+    std::vector<cudaStream_t> streams[kMaxDevices];
+    std::vector<cudaEvent_t> events[kMaxDevices];
+    DeviceInfo info[kMaxDevices];
+    size_t cachedDevice[kMaxDevices] = {0}, cachedPinned = 0;
 };
 ResourceCache& cache() { static ResourceCache* c = new ResourceCache(); return *c; }  // leaked on purpose: no teardown order issues
 constexpr size_t kMaxCachedDevice = 8ull << 30, kMaxCachedPinned = 2ull << 30;
@@ -112,7 +112,7 @@ bool device_alloc(int device, void** p, size_t bytes) {
     {
         std::lock_guard<std::mutex> lk(c.mu);
         size_t got = 0;
-        if (take_block(c.freeDevice[device & 15], bytes, p, &got)) { c.cachedDevice[device & 15] -= got; c.liveBytes[*p] = got; return true; }
+        if (take_block(c.freeDevice[device], bytes, p, &got)) { c.cachedDevice[device] -= got; c.liveBytes[*p] = got; return true; }
     }
     CUDA_TRY(cudaMalloc(p, bytes));
     std::lock_guard<std::mutex> lk(c.mu);
@@ -125,9 +125,9 @@ void device_release(int device, void* p) {
     std::lock_guard<std::mutex> lk(c.mu);
     const size_t bytes = c.liveBytes[p];
     c.liveBytes.erase(p);
-    if (c.cachedDevice[device & 15] + bytes > kMaxCachedDevice) { cudaFree(p); return; }
-    c.freeDevice[device & 15].push_back({p, bytes});
-    c.cachedDevice[device & 15] += bytes;
+    if (c.cachedDevice[device] + bytes > kMaxCachedDevice) { cudaFree(p); return; }
+    c.freeDevice[device].push_back({p, bytes});
+    c.cachedDevice[device] += bytes;
 }
 static bool pinned_alloc(void** p, size_t bytes) {
     bytes = std::max<size_t>(bytes, 256);
@@ -152,11 +152,34 @@ static void pinned_release(void* p) {
     c.freePinned.push_back({p, bytes});
     c.cachedPinned += bytes;
 }
+// Returns every cached (not live) device and pinned block to the driver.
+void trim_cache() {
+    ResourceCache& c = cache();
+    std::vector<std::pair<int, void*>> dev;
+    std::vector<void*> pinned;
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        for (int d = 0; d < kMaxDevices; d++) {
+            for (const CachedBlock& b : c.freeDevice[d]) dev.push_back({d, b.p});
+            c.freeDevice[d].clear();
+            c.cachedDevice[d] = 0;
+        }
+        for (const CachedBlock& b : c.freePinned) pinned.push_back(b.p);
+        c.freePinned.clear();
+        c.cachedPinned = 0;
+    }
+    int saved = -1;
+    if (cudaGetDevice(&saved) != cudaSuccess) saved = -1;
+    for (const auto& b : dev) { cudaSetDevice(b.first); cudaFree(b.second); }
+    for (void* p : pinned) cudaFreeHost(p);
+    if (saved >= 0) cudaSetDevice(saved);
+}
+
 static bool stream_acquire(int device, cudaStream_t* s) {
     ResourceCache& c = cache();
     {
         std::lock_guard<std::mutex> lk(c.mu);
-        auto& v = c.streams[device & 15];
+        auto& v = c.streams[device];
         if (!v.empty()) { *s = v.back(); v.pop_back(); return true; }
     }
     CUDA_TRY(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
@@ -166,13 +189,13 @@ static void stream_release(int device, cudaStream_t s) {
     if (!s) return;
     ResourceCache& c = cache();
     std::lock_guard<std::mutex> lk(c.mu);
-    c.streams[device & 15].push_back(s);
+    c.streams[device].push_back(s);
 }
 static bool event_acquire(int device, cudaEvent_t* e) {
     ResourceCache& c = cache();
     {
         std::lock_guard<std::mutex> lk(c.mu);
-        auto& v = c.events[device & 15];
+        auto& v = c.events[device];
         if (!v.empty()) { *e = v.back(); v.pop_back(); return true; }
     }
     CUDA_TRY(cudaEventCreate(e));
@@ -182,13 +205,13 @@ static void event_release(int device, cudaEvent_t e) {
     if (!e) return;
     ResourceCache& c = cache();
     std::lock_guard<std::mutex> lk(c.mu);
-    c.events[device & 15].push_back(e);
+    c.events[device].push_back(e);
 }
 static bool device_info(int device, DeviceInfo* out) {
     ResourceCache& c = cache();
     {
         std::lock_guard<std::mutex> lk(c.mu);
-        if (c.info[device & 15].known) { *out = c.info[device & 15]; return true; }
+        if (c.info[device].known) { *out = c.info[device]; return true; }
     }
     DeviceInfo di;
     CUDA_TRY(cudaDeviceGetAttribute(&di.numSMs, cudaDevAttrMultiProcessorCount, device));
@@ -196,7 +219,7 @@ static bool device_info(int device, DeviceInfo* out) {
     CUDA_TRY(cudaDeviceGetAttribute(&di.major, cudaDevAttrComputeCapabilityMajor, device));
     di.known = true;
     std::lock_guard<std::mutex> lk(c.mu);
-    c.info[device & 15] = di;
+    c.info[device] = di;
     *out = di;
     return true;
 }
@@ -553,12 +576,17 @@ static __global__ void pack_pairs_kernel(const uint8_t* residues, const long lon
             const long long c = e - pairOffsets[p];
             const int a = 2 * p, b = 2 * p + 1;
             if (c >= 0 && c < lengths[a]) {
-                word = (uint32_t)residues[offsets[a] + c] + 1u;
-                if (b < numTargets && c < lengths[b]) word |= ((uint32_t)residues[offsets[b] + c] + 1u) << 8;
+                const uint32_t r0 = (uint32_t)residues[offsets[a] + c] + 1u;
+                word = r0 & 0xffu;
+                mx = max(mx, r0);  // from the raw residue: code 255 (+ 1) does not fit the byte and is searched at 32 bits
+                if (b < numTargets && c < lengths[b]) {
+                    const uint32_t r1 = (uint32_t)residues[offsets[b] + c] + 1u;
+                    word |= (r1 & 0xffu) << 8;
+                    mx = max(mx, r1);
+                }
             }
         }
         pairStream[e] = (uint16_t)word;
-        mx = max(mx, max(word & 0xffu, word >> 8));
     }
     mx = __reduce_max_sync(0xffffffffu, mx);
     if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&blockMax, (int)mx);
@@ -625,7 +653,7 @@ bool DeviceDb::alloc_search_buffers() {
 // order[p]) is given.  Returns with the upload in flight on the database's stream (see ensure_uploaded()).
 DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed, const int* lens, const int* order, int n, int device) {
     int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count || device >= kMaxDevices) {
         set_error("no usable CUDA device");
         return nullptr;
     }
@@ -989,6 +1017,20 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
     return true;
 }
 
+// The dynamic shared-memory ceiling of a kernel is per-function state shared by every host thread (search_batch runs
+// up to eight of them over the same kernels): it is raised once per (device, kernel) to the device limit instead of
+// being set to each launch's size, which another thread could lower between one thread's set and its launch.
+static bool allow_full_smem(int device, const void* fn, int smemLimit) {
+    static std::mutex mu;
+    static std::vector<std::pair<int, const void*>> done;
+    std::lock_guard<std::mutex> lk(mu);
+    for (const auto& d : done)
+        if (d.first == device && d.second == fn) return true;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smemLimit));
+    done.push_back({device, fn});
+    return true;
+}
+
 // Launches every pass of one group on `stream`.
 bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t stream, const unsigned char* dQuery,
                             const int* dMatrix, int Q, int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot) {
@@ -1010,7 +1052,7 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
     const void* fn = kernel_tables()[g.tableIndex].fn[type * 4 + flavor];
     if (flavor == kFlavorGlobal && 128 * g.warpsPerPartition > launch_bound_for(flavor, g.R))
         fn = kernel_tables()[g.tableIndex].fn[type == 0 ? 8 : type * 4 + flavor];  // Packed16 variant compiled for 384 threads
-    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grp.smemBytes));
+    if (!allow_full_smem(device_, fn, smemLimit_)) return false;
     for (int pass = 0; pass < g.passes; pass++) {
         SearchParams p;
         memset(&p, 0, sizeof(p));
@@ -1087,13 +1129,14 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
                     g.g.folded ? " folded" : "", g.tasks.size(),
                     g.tasks.empty() ? 0 : sortedLen_[g.type == 0 && !g.g.folded ? 2 * g.tasks[0] : g.tasks[0]], g.g.G, g.g.R,
                     g.g.warpsPerPartition, g.g.passes, g.maxBlocks, g.estCycles / 1e3);
+    bool badArgument = false;
     auto body = [&]() -> bool {
         size_t listOffset = 0;
         // create() returns with the upload in flight; planning above ran beside it.  The residue codes are
         // validated here, before anything indexes the profile with them.
         if (!ensure_uploaded()) return false;
         trace.mark("upload-wait");
-        if (maxCode_ >= A) { set_error("database holds residue codes >= alphabetLength"); return false; }
+        if (maxCode_ >= A) { set_error("database holds residue codes >= alphabetLength"); badArgument = true; return false; }
         if (!startRecorded_) { CUDA_TRY(cudaEventRecord(evStart_, stream_)); startRecorded_ = true; }  // planning is host work: keep it outside the device window
         if (groups.size() > 1) CUDA_TRY(cudaEventRecord(evFork_, stream_));
         for (size_t gi = 0; gi < groups.size(); gi++) {
@@ -1117,7 +1160,7 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
         }
         return true;
     };
-    return body() ? 0 : OPAL_B200_ERR_CUDA;
+    return body() ? 0 : (badArgument ? OPAL_B200_ERR_ARGUMENT : OPAL_B200_ERR_CUDA);
 }
 
 int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const int* matrix, int A, int wantEnd, int mode,
@@ -1126,7 +1169,15 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
     PhaseTrace trace("search");
     if (deviceMs) *deviceMs = 0.f;
     if (mode != kModeNW && mode != kModeHW && mode != kModeOV && mode != kModeSW) return OPAL_B200_ERR_MODE;
-    if (A <= 0 || A > 254) { set_error("alphabetLength must be in [1, 254]"); return OPAL_B200_ERR_CUDA; }
+    // Any unsigned char alphabet (reference src/opal.h:96-98).  The 16-bit streams store residue code + 1 in a byte, so
+    // code 255 cannot ride in them: a database that really holds it (alphabetLength 256) is searched by the 32-bit
+    // class, which reads the plain stream.
+    if (A <= 0 || A > 256) { set_error("alphabetLength must be in [1, 256]"); return OPAL_B200_ERR_ARGUMENT; }
+    bool wideCodes = false;
+    if (A == 256) {
+        if (!ensure_uploaded()) return OPAL_B200_ERR_CUDA;
+        wideCodes = maxCode_ >= 255;
+    }
     // Argument range of the widest pass (reference src/opal.cpp:183-198, 615-630).
     if (Go <= INT_MIN / 2 || INT_MAX / 2 <= Go || Ge <= INT_MIN / 2 || INT_MAX / 2 <= Ge) return OPAL_B200_ERR_OVERFLOW;
     int maxP = INT_MIN, minP = INT_MAX;
@@ -1137,13 +1188,13 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
     }
     const long long absP = std::max<long long>(std::llabs((long long)maxP), std::llabs((long long)minP));
     const long long gapMax = std::max<long long>(std::llabs((long long)Go), std::llabs((long long)Ge));
-    if (Go < 0 || Ge < 0) { set_error("gap penalties must be non-negative"); return OPAL_B200_ERR_OVERFLOW; }
-    const bool args16 = absP <= 2048 && gapMax <= 2048;
+    if (Go < 0 || Ge < 0) { set_error("gap penalties must be non-negative"); return OPAL_B200_ERR_ARGUMENT; }
+    const bool args16 = absP <= 2048 && gapMax <= 2048 && !wideCodes;
     const bool args32 = absP < (1 << 28) && gapMax < (1 << 28);
     if (!args32) return OPAL_B200_ERR_OVERFLOW;  // beyond the widths this engine carries (documented deviation)
 
     for (int r = 0; r < Q; r++)
-        if (query[r] >= A) { set_error("query holds residue codes >= alphabetLength"); return OPAL_B200_ERR_CUDA; }
+        if (query[r] >= A) { set_error("query holds residue codes >= alphabetLength"); return OPAL_B200_ERR_ARGUMENT; }
 
     // ---- per-target routing
     const bool isSW = mode == kModeSW;
@@ -1153,6 +1204,12 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
         const long long hi = (maxP > 0 ? (long long)std::min(Q, T) * maxP : 0) + Go + absP;
         return lo <= lim && hi <= lim;
     };
+    // HW / OV track the last query row in EVERY column a pair sweeps, the pad columns of its shorter member
+    // included.  A pad cell is max(diag + padLetterScore, E, F) with padLetterScore = -16384 at 16 bits, and DPX adds
+    // wrap: diag must stay above -16384 or the cell turns into a large positive "score" of the shorter target.  A pair
+    // is never split between the classes (below), so bounding every member by 16383 bounds the longer one, whose
+    // length the pad columns run to.  NW reads one cell per target (pad columns come after it) and keeps 28000.
+    const long long lim16 = mode == kModeNW ? 28000 : 16383;
     std::vector<int> list16, list32;
     (args16 ? list16 : list32).reserve((size_t)n_);
     bool touched = false;
@@ -1162,7 +1219,8 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
         const int T = sortedLen_[p];
         if (T == 0 || Q <= 0) {  // nothing to align: defined as in oracle/opal_oracle.c
             int sc = 0, eq = Q - 1, et = T - 1;
-            if (Q > 0 && (mode == kModeNW || mode == kModeHW)) sc = -Go - (Q - 1) * Ge;
+            if (Q > 0 && (mode == kModeNW || mode == kModeHW)) sc = -Go - (Q - 1) * Ge;  // the query against one gap
+            else if (Q <= 0 && T > 0 && mode == kModeNW) sc = -Go - (T - 1) * Ge;         // ... and the target against one
             if (isSW) { eq = -1; et = -1; }
             scores[i] = sc;
             if (endQ) endQ[i] = wantEnd ? eq : -1;
@@ -1175,7 +1233,7 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
             else if ((maxP > 0 ? (long long)std::min(Q, T) * maxP : 0) < (1LL << 30)) list32.push_back(p);
             else return OPAL_B200_ERR_OVERFLOW;
         } else {
-            if (args16 && fits(T, 28000)) list16.push_back(p);
+            if (args16 && fits(T, lim16)) list16.push_back(p);
             else if (fits(T, 1LL << 30)) list32.push_back(p);
             else return OPAL_B200_ERR_OVERFLOW;
         }
@@ -1257,7 +1315,7 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
         if (!isSW && !list32.empty()) first.push_back({1, &list32});
         if (!first.empty()) {
             rc = run_classes(first, dQuery, dMatrix, Q, Go, Ge, A, wantEnd, mode, maxP, &slot);
-            if (rc) return rc != OPAL_B200_ERR_CUDA;
+            if (rc) return rc != OPAL_B200_ERR_CUDA;  // a CUDA failure has set the error text; other codes pass through
             CUDA_TRY(cudaEventRecord(evStop_, stream_));
             if (!fetch()) return false;
             std::vector<int> again;
@@ -1273,7 +1331,7 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
         if (isSW && !list32.empty()) {
             std::vector<std::pair<int, const std::vector<int>*>> second = {{1, &list32}};
             rc = run_classes(second, dQuery, dMatrix, Q, Go, Ge, A, wantEnd, mode, maxP, &slot);
-            if (rc) return rc != OPAL_B200_ERR_CUDA;
+            if (rc) return rc != OPAL_B200_ERR_CUDA;  // a CUDA failure has set the error text; other codes pass through
             CUDA_TRY(cudaEventRecord(evStop_, stream_));
             if (!fetch()) return false;
             publish(list32, nullptr);
@@ -1341,7 +1399,7 @@ int DeviceDb::search_batch(int numQueries, const unsigned char* const* queries, 
 }
 
 // ------------------------------------------------------------------ DPX roofline probe
-double measure_dpx_peak(int device, double* threadInstrPerSec, float* msOut) {
+double measure_dpx_peak(int device, int mix, double* threadInstrPerSec, float* msOut) {
     constexpr int ILP = 8;
     const int iters = 4096;
     if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return 0.0; }
@@ -1355,7 +1413,8 @@ double measure_dpx_peak(int device, double* threadInstrPerSec, float* msOut) {
     float best = 1e30f;
     for (int rep = 0; rep < 5; rep++) {
         cudaEventRecord(a);
-        dpx_peak_kernel<ILP><<<blocks, 512>>>(out, iters, 12345u + rep);
+        if (mix == 0) dpx_peak_kernel<ILP, 0><<<blocks, 512>>>(out, iters, 12345u + rep);
+        else dpx_peak_kernel<ILP, 1><<<blocks, 512>>>(out, iters, 12345u + rep);
         cudaEventRecord(b);
         cudaEventSynchronize(b);
         float ms = 0;
@@ -1365,11 +1424,12 @@ double measure_dpx_peak(int device, double* threadInstrPerSec, float* msOut) {
     const cudaError_t e = cudaGetLastError();
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return 0.0; }
-    const double instr = 6.0 * ILP * (double)iters * blocks * 512;  // thread-level packed instructions
+    const double perPair = mix == 0 ? 6.0 : 5.0;  // packed instructions per cell pair: SW / NW-HW-OV
+    const double instr = perPair * ILP * (double)iters * blocks * 512;  // thread-level packed instructions
     const double ips = instr / (best * 1e-3);
     if (threadInstrPerSec) *threadInstrPerSec = ips;
     if (msOut) *msOut = best;
-    return ips * 2.0 / 6.0 / 1e9;  // 2 cells per packed instruction, 6 instructions per SW cell pair
+    return ips * 2.0 / perPair / 1e9;  // 2 cells per packed instruction
 }
 
 }  // namespace opalb200

@@ -11,7 +11,7 @@
 namespace opalb200 {
 
 // Return codes shared with opal.h (OPAL_ERR_OVERFLOW / _NO_SIMD_SUPPORT / _INVALID_MODE).
-constexpr int OPAL_B200_ERR_OVERFLOW = 1, OPAL_B200_ERR_CUDA = 2, OPAL_B200_ERR_MODE = 3;
+constexpr int OPAL_B200_ERR_OVERFLOW = 1, OPAL_B200_ERR_CUDA = 2, OPAL_B200_ERR_MODE = 3, OPAL_B200_ERR_ARGUMENT = 4;
 // Folded stream: at most this many of the longest targets, none shorter than kFoldMinLength.
 constexpr int kFoldTargets = 128, kFoldMinLength = 256;
 
@@ -33,9 +33,11 @@ struct SearchStats {
     int kernelLaunches = 0, rerun32 = 0, G = 0, R = 0, passes = 0, warpsPerPartition = 0, groups = 0, foldedTasks = 0;
 };
 
-// Device memory from the per-device block cache (engine.cu): recycled, not returned to the driver.
+constexpr int kMaxDevices = 64;  // devices the per-device resource cache is sized for (larger ordinals are rejected)
+// Device memory from the per-device block cache (engine.cu): recycled, not returned to the driver (until trim_cache()).
 bool device_alloc(int device, void** p, size_t bytes);
 void device_release(int device, void* p);
+void trim_cache();
 
 // body(lo, hi) over [0, n) in parts of at least `grain`, on the persistent host pool (the caller takes part).
 void parallel_for(long long n, long long grain, const std::function<void(long long, long long)>& body);
@@ -124,6 +126,6 @@ private:
     bool startRecorded_ = false;
 };
 
-double measure_dpx_peak(int device, double* threadInstrPerSec, float* ms);
+double measure_dpx_peak(int device, int mix, double* threadInstrPerSec, float* ms);  // mix 0 = SW recurrence, 1 = NW / HW / OV
 
 }  // namespace opalb200

@@ -752,9 +752,10 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
 }
 
 // ---------------------------------------------------------------- DPX issue-rate probe
-// Register-only loop of the SW cell recurrence (6 packed instructions per 2 cells) used by
-// bench.py to measure the integer-pipe roofline on the device it runs on.
-template <int ILP>
+// Register-only loop of the cell recurrence used by bench.py to measure the integer-pipe roofline on the
+// device it runs on.
+// MIX 0: the SW recurrence, 6 packed instructions per 2 cells; MIX 1: NW / HW / OV, 5 (no running maximum per cell).
+template <int ILP, int MIX>
 __global__ void __launch_bounds__(512, 1) dpx_peak_kernel(uint32_t* out, int iters, uint32_t seed) {
     uint32_t h[ILP], e[ILP], f[ILP], b[ILP];
 #pragma unroll
@@ -765,9 +766,9 @@ __global__ void __launch_bounds__(512, 1) dpx_peak_kernel(uint32_t* out, int ite
         for (int i = 0; i < ILP; i++) {
             e[i] = __viaddmax_s16x2(e[i], ng, h[i]);
             f[i] = __viaddmax_s16x2(f[i], ng, h[i]);
-            uint32_t x = __viaddmax_s16x2_relu(h[i], pp, e[i]);
+            uint32_t x = MIX == 0 ? __viaddmax_s16x2_relu(h[i], pp, e[i]) : __viaddmax_s16x2(h[i], pp, e[i]);
             x = __vmaxs2(x, f[i]);
-            b[i] = __vmaxs2(b[i], x);
+            if (MIX == 0) b[i] = __vmaxs2(b[i], x);
             h[i] = __vadd2(x, no);
         }
     }

@@ -50,6 +50,10 @@ class OpalB200(OpalCLibrary):
         L.opalb200_db_last_folded.restype = ci
         L.opalb200_measure_dpx_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]
         L.opalb200_measure_dpx_peak.restype = ctypes.c_double
+        L.opalb200_measure_dpx_peak_mix.argtypes = [ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]
+        L.opalb200_measure_dpx_peak_mix.restype = ctypes.c_double
+        L.opalb200_trim_cache.argtypes = []
+        L.opalb200_trim_cache.restype = None
 
     def device_count(self):
         return int(self.lib.opalb200_device_count())
@@ -75,9 +79,13 @@ class OpalB200(OpalCLibrary):
             raise RuntimeError("opalb200_db_create_sorted failed: " + self.last_error())
         return ResidentDb(self, h, int(lens.size))
 
-    def measure_dpx_peak(self, device=0):
+    def trim_cache(self):
+        self.lib.opalb200_trim_cache()
+
+    def measure_dpx_peak(self, device=0, mix=0):
+        """(GCUPS the integer pipe can sustain, packed thread-instructions/s, kernel ms); mix 0 = SW, 1 = NW/HW/OV."""
         ips, ms = ctypes.c_double(0), ctypes.c_float(0)
-        g = self.lib.opalb200_measure_dpx_peak(int(device), ctypes.byref(ips), ctypes.byref(ms))
+        g = self.lib.opalb200_measure_dpx_peak_mix(int(device), int(mix), ctypes.byref(ips), ctypes.byref(ms))
         if g <= 0:
             raise RuntimeError("DPX probe failed: " + self.last_error())
         return float(g), float(ips.value), float(ms.value)
@@ -106,17 +114,22 @@ class ResidentDb:
             sc.ctypes.data, eq.ctypes.data, et.ctypes.data, ctypes.byref(ms))
         return rc, sc, eq, et, float(ms.value)
 
-    def search_batch(self, queries, gap_open, gap_ext, score_matrix, alphabet_length, search_type, mode, in_flight=3):
-        """opalb200_db_search_batch. Returns (rc, scores[nq, n], endQuery, endTarget, batch_ms)."""
+    def search_batch(self, queries, gap_open, gap_ext, score_matrix, alphabet_length, search_type, mode, in_flight=3, out=None):
+        """opalb200_db_search_batch. Returns (rc, scores[nq, n], endQuery, endTarget, batch_ms); `out` = three
+        preallocated int32 [nq, n] arrays to write into (entries that are not computed keep their old values)."""
         qs = [np.ascontiguousarray(q, dtype=np.uint8) for q in queries]
         qs = [q if q.size else np.zeros(1, dtype=np.uint8) for q in qs]
         nq = len(qs)
         ptrs = np.array([q.ctypes.data for q in qs], dtype=np.uint64)
         qlens = np.array([len(q) for q in queries], dtype=np.int32)
         sm = np.ascontiguousarray(score_matrix, dtype=np.int32).ravel()
-        sc = np.zeros((nq, self.n), dtype=np.int32)
-        eq = np.full((nq, self.n), -1, dtype=np.int32)
-        et = np.full((nq, self.n), -1, dtype=np.int32)
+        if out is not None:
+            sc, eq, et = out
+            assert all(a.shape == (nq, self.n) and a.dtype == np.int32 and a.flags["C_CONTIGUOUS"] for a in out)
+        else:
+            sc = np.zeros((nq, self.n), dtype=np.int32)
+            eq = np.full((nq, self.n), -1, dtype=np.int32)
+            et = np.full((nq, self.n), -1, dtype=np.int32)
         ms = ctypes.c_float(0)
         if isinstance(mode, str):
             mode = MODES[mode]

@@ -141,6 +141,7 @@ int oracle_score_end(const unsigned char* q, int Q, const unsigned char* t, int 
         if (mode == OPAL_MODE_NW) {
             if (T > 0 && Q > 0) best = H;
             else if (Q > 0) best = -(i64)Go - (i64)(Q - 1) * Ge; /* empty target: query against gaps */
+            else if (T > 0) best = -(i64)Go - (i64)(T - 1) * Ge;  /* empty query: target against gaps */
             else best = 0;
             bq = Q - 1; bt = T - 1;
         } else if (best == NEG_INF) { /* empty target or query: nothing aligned */

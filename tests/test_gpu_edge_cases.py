@@ -37,7 +37,11 @@ def test_empty_database_and_invalid_arguments(product):
     rc, _ = product.search_database(q, db, 5, 2, big, 4)
     assert rc == 1
     rc, _ = product.search_database(np.array([0, 7], dtype=np.uint8), db, 5, 2, sm.flat(), 4)
-    assert rc == 2 and "alphabetLength" in product.last_error()  # defined failure instead of the reference's wild read
+    assert rc == 4 and "alphabetLength" in product.last_error()  # OPAL_ERR_INVALID_ARGUMENT instead of the reference's wild read
+    rc, _ = product.search_database(q, db, -1, 2, sm.flat(), 4)
+    assert rc == 4 and "gap" in product.last_error()
+    rc, _ = product.search_database(q, SequenceDB.from_sequences([[0, 1, 5]]), 5, 2, sm.flat(), 4)
+    assert rc == 4 and "database" in product.last_error()
 
 
 @pytest.mark.parametrize("mode", ["SW", "NW"])
@@ -158,3 +162,36 @@ def test_config5_miniature_long_dna_query_many_passes(product, oracle, mode, go,
         assert got == want, [(i, g, w) for i, (g, w) in enumerate(zip(got, want)) if g != w][:3]
     if mode == "SW":
         assert max(w[1] for w in want) > 32767  # the planted copies really leave the 16-bit range
+
+
+@pytest.mark.parametrize("mode", ["HW", "OV", "NW"])
+def test_long_query_against_unequal_short_pair_16_bit_pad_columns(product, oracle, mode):
+    """a pair of unequal lengths sweeps pad columns for its shorter member; with H below -16384 the pad
+    cell (diag - 16384) used to wrap into a large positive last-row value at 16 bits.  Q * gapExt > 17000 here."""
+    rng = np.random.default_rng(77)
+    sm = matrices.blosum62()
+    q = datasets.random_residues(20000, rng, sm)
+    seqs = [datasets.random_residues(n, rng, sm) for n in (500, 400, 900, 350, 120, 119, 64, 3)]
+    db = SequenceDB.from_sequences(seqs)
+    for st in (0, 1):
+        _same(product, oracle, q, db, 11, 1, sm.flat(), 23, mode, st)
+
+
+@pytest.mark.parametrize("top", [254, 255])
+def test_alphabet_255_and_256(product, oracle, top):
+    """Any unsigned char alphabet (reference src/opal.h:96-98): alphabetLength 255 and 256, with and without the
+    residue code 255 (which cannot ride in the 16-bit streams and is searched by the 32-bit class)."""
+    rng = np.random.default_rng(5 + top)
+    for A in (255, 256):
+        if top >= A:
+            continue
+        matrix = rng.integers(-4, 3, (A, A)).astype(np.int32)
+        matrix[np.arange(A), np.arange(A)] = 5
+        q = rng.integers(0, A, 90).astype(np.uint8)
+        q[3] = A - 1
+        seqs = [rng.integers(0, top + 1, int(n)).astype(np.uint8) for n in rng.integers(1, 300, 60)]
+        seqs[7][0] = top
+        seqs[11] = q[10:80].copy()
+        db = SequenceDB.from_sequences(seqs)
+        for mode in ("SW", "NW", "HW", "OV"):
+            _same(product, oracle, q, db, 7, 2, matrix.ravel(), A, mode, 1)

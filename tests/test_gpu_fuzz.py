@@ -1,4 +1,4 @@
-"""Seeded random parity sweep of the CUDA path against the oracle through the C ABI: alphabets from 2 to 254 letters,
+"""Seeded random parity sweep of the CUDA path against the oracle through the C ABI: alphabets from 2 to 256 letters,
 asymmetric matrices with small to huge entries (16-bit lanes, overflow re-runs and a-priori 32-bit routing), gap
 penalties including gapExt = 0 and gapOpen < gapExt, query lengths from 1 to several strips of rows, ragged targets
 including empty ones.  Every record field is compared, for all four modes and both score levels."""
@@ -9,7 +9,7 @@ from _util import MODES, SequenceDB, search_dump
 
 pytestmark = pytest.mark.gpu
 
-ALPHABETS = (2, 4, 7, 20, 23, 24, 60, 254)
+ALPHABETS = (2, 4, 7, 20, 23, 24, 60, 254, 255, 256)
 MAGNITUDES = (1, 5, 20, 127, 2000, 40000)
 
 
@@ -38,7 +38,7 @@ def _case(seed):
     return q, SequenceDB.from_sequences(seqs), go, ge, matrix.ravel(), A
 
 
-@pytest.mark.parametrize("seed", range(36))
+@pytest.mark.parametrize("seed", range(48))
 def test_random_parameters_match_the_oracle(product, oracle, seed):
     q, db, go, ge, matrix, A = _case(seed)
     mode = ("NW", "HW", "OV", "SW")[seed % 4]

@@ -101,7 +101,7 @@ def test_batch_reports_errors(product):
     h = product.create_db(db, 0)
     try:
         rc, *_ = h.search_batch([np.array([0, 1], np.uint8), np.array([0, 9], np.uint8)], 5, 2, sm.flat(), 4, 0, "SW")
-        assert rc == 2 and "alphabetLength" in product.last_error()
+        assert rc == 4 and "alphabetLength" in product.last_error()
         rc, S, *_ = h.search_batch([], 5, 2, sm.flat(), 4, 0, "SW")
         assert rc == 0 and S.shape == (0, 2)
     finally:
