@@ -39,6 +39,20 @@ void opalb200_trim_cache(void);
  */
 OpalB200Db* opalb200_db_create(unsigned char* db[], int dbLength, const int dbSeqLengths[], int device);
 /*
+ * The same database resident on SEVERAL devices of this host: the sequences, in length order, are dealt round-robin
+ * over devices[0 .. numDevices) -- shards of equal residue count (= equal work: cells = queryLength x residues) and
+ * equal length mix -- and every search below runs on all of them concurrently, one host thread and one set of
+ * streams per device, each device returning its own results, which are scattered into the caller's arrays by an
+ * index map (targets are independent: no collective, no peer traffic).  The alignment stage of
+ * a target runs on the device that owns it.  opalb200_db_create / _create_sorted with device = -1 take the devices
+ * from the environment instead (OPAL_B200_DEVICES = "all" or "0,1,...", else OPAL_B200_DEVICE, else device 0) -- as
+ * the drop-in opalSearchDatabase does, which has no device argument.  devices NULL or numDevices <= 0: likewise.
+ */
+OpalB200Db* opalb200_db_create_multi(unsigned char* db[], int dbLength, const int dbSeqLengths[], const int devices[],
+                                     int numDevices);
+/* Devices the handle's database is dealt over (1 unless created for several). */
+int opalb200_db_devices(const OpalB200Db* handle);
+/*
  * Same, from a database that is already packed (the in-memory form of the on-disk format written by
  * opal_makedb_b200, opal_b200/cli/packed_db.h; replaces the per-run parse + sort of readFastaSequences,
  * reference src/opal_aligner.cpp:247-301): `residues` holds all sequences back to back, longest first;

@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/opal.h"
@@ -28,6 +30,128 @@ struct DeviceGuard {
 static int default_device() {
     const char* e = getenv("OPAL_B200_DEVICE");
     return e ? atoi(e) : 0;
+}
+
+// ------------------------------------------------------------------ several devices behind one call
+// Every (query, target) pair is independent: a database is dealt over the devices, each device
+// searches its shard on a host thread and streams of its own, results come back by per-device copies and are
+// scattered into the caller's arrays by an index map.  No collective, no peer traffic.
+
+// Devices of the drop-in entry points (they take no device argument): OPAL_B200_DEVICES = "all" or a comma-separated
+// list of ordinals; otherwise the single device OPAL_B200_DEVICE (default 0).
+static std::vector<int> env_devices() {
+    std::vector<int> devs;
+    if (const char* e = getenv("OPAL_B200_DEVICES")) {
+        if (!strcmp(e, "all")) {
+            int count = 0;
+            if (cudaGetDeviceCount(&count) != cudaSuccess) count = 0;
+            for (int d = 0; d < count; d++) devs.push_back(d);
+        } else {
+            for (const char* p = e; *p;) {
+                char* end = nullptr;
+                const long d = strtol(p, &end, 10);
+                if (end == p) break;
+                if (d >= 0) devs.push_back((int)d);  // an ordinal may repeat: several shards on one device (used by the tests)
+                p = *end ? end + 1 : end;
+            }
+        }
+    }
+    if (devs.empty()) devs.push_back(default_device());
+    return devs;
+}
+
+// Shards balanced by residue count: the sequences in length order (longest first, ties in caller order) are dealt
+// round-robin, so every shard also gets the same length mix -- its longest target is about as long as the others'.
+// index[s] lists the caller indices of shard s in ascending order (sequential reads of the caller's memory).
+static void deal_shards(const int* lens, int n, int parts, std::vector<std::vector<int>>* index) {
+    std::vector<int> order((size_t)n);
+    int maxLen = 0;
+    for (int i = 0; i < n; i++) maxLen = std::max(maxLen, lens[i]);
+    if (maxLen <= (1 << 22)) {  // counting sort
+        std::vector<int> start((size_t)maxLen + 2, 0);
+        for (int i = 0; i < n; i++) start[maxLen - std::max(lens[i], 0) + 1]++;
+        for (int k = 1; k <= maxLen + 1; k++) start[k] += start[k - 1];
+        for (int i = 0; i < n; i++) order[start[maxLen - std::max(lens[i], 0)]++] = i;
+    } else {
+        for (int i = 0; i < n; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
+    }
+    index->assign((size_t)parts, std::vector<int>());
+    for (auto& v : *index) v.reserve((size_t)n / parts + 1);
+    for (int p = 0; p < n; p++) (*index)[p % parts].push_back(order[p]);
+    for (auto& v : *index) std::sort(v.begin(), v.end());
+}
+
+// fn(s) for every shard, each on a host thread of its own (the caller runs shard 0); returns the first non-zero
+// code in shard order and leaves that shard's error text with the calling thread.
+template <class F>
+static int on_shards(int parts, F fn) {
+    if (parts == 1) return fn(0);
+    std::vector<int> rc((size_t)parts, 0);
+    std::vector<std::string> err((size_t)parts);
+    std::vector<std::thread> th;
+    for (int s = 1; s < parts; s++)
+        th.emplace_back([&, s] {
+            DeviceGuard guard;
+            rc[s] = fn(s);
+            if (rc[s]) err[s] = last_error();
+        });
+    rc[0] = fn(0);
+    if (rc[0]) err[0] = last_error();
+    for (auto& t : th) t.join();
+    for (int s = 0; s < parts; s++)
+        if (rc[s]) { set_error(err[s]); return rc[s]; }
+    return 0;
+}
+
+// The object behind an OpalB200Db handle: one resident shard per device.
+struct DbHandle {
+    std::vector<DeviceDb*> shards;
+    std::vector<std::vector<int>> index;  // [shard][local index] -> caller index; empty when one shard holds everything
+    int n = 0;
+    long long residues = 0;
+    SearchStats stats;  // last search: launches / re-runs summed over the shards, geometry of shard 0
+    ~DbHandle() { for (DeviceDb* d : shards) delete d; }
+    int parts() const { return (int)shards.size(); }
+    int caller_index(int s, int local) const { return index.empty() ? local : index[s][local]; }
+    void collect_stats() {
+        stats = shards[0]->stats();
+        for (size_t s = 1; s < shards.size(); s++) {
+            stats.kernelLaunches += shards[s]->stats().kernelLaunches;
+            stats.rerun32 += shards[s]->stats().rerun32;
+            stats.foldedTasks += shards[s]->stats().foldedTasks;
+        }
+    }
+};
+
+// Shards of `n` scattered sequences on `devices`: NULL (error text set) on failure.
+static DbHandle* create_handle(unsigned char* const* db, int n, const int* lens, const std::vector<int>& devices,
+                               const int* callerIndex = nullptr) {
+    DbHandle* h = new DbHandle();
+    h->n = n;
+    const int parts = (int)std::max<size_t>(1, std::min<size_t>(devices.size(), (size_t)std::max(n / 2, 1)));
+    h->shards.assign((size_t)parts, nullptr);
+    if (parts == 1 && !callerIndex) {
+        h->shards[0] = DeviceDb::create(db, n, lens, devices[0]);
+        if (!h->shards[0]) { delete h; return nullptr; }
+        h->residues = h->shards[0]->residues();
+        return h;
+    }
+    deal_shards(lens, n, parts, &h->index);
+    const int rc = on_shards(parts, [&](int s) -> int {
+        const std::vector<int>& idx = h->index[s];
+        std::vector<unsigned char*> ptr(idx.size());
+        std::vector<int> len(idx.size());
+        for (size_t k = 0; k < idx.size(); k++) { ptr[k] = db[idx[k]]; len[k] = lens[idx[k]]; }
+        h->shards[s] = DeviceDb::create(ptr.data(), (int)idx.size(), len.data(), devices[s]);
+        return h->shards[s] ? 0 : OPAL_ERR_NO_SIMD_SUPPORT;
+    });
+    if (rc) { delete h; return nullptr; }
+    for (DeviceDb* d : h->shards) h->residues += d->residues();
+    if (callerIndex)  // the sequences came in an order of their own (packed database): translate to the caller's
+        for (auto& v : h->index)
+            for (int& i : v) i = callerIndex[i];
+    return h;
 }
 
 extern "C" {
@@ -51,7 +175,7 @@ void opalSearchResultSetScore(OpalSearchResult* r, int score) {  // :1561-1564
 // then created from db / dbSeqLengths if any entry needs work.  db / dbSeqLengths may be NULL for handle calls.
 static int search_into_results(DeviceDb* ddb, const unsigned char* query, int queryLength, unsigned char* const* db, int dbLength,
                                const int* dbSeqLengths, int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength,
-                               OpalSearchResult* results[], const int searchType, int mode) {
+                               OpalSearchResult* results[], const int searchType, int mode, int device) {
     if (mode != OPAL_MODE_NW && mode != OPAL_MODE_HW && mode != OPAL_MODE_OV && mode != OPAL_MODE_SW)
         return OPAL_ERR_INVALID_MODE;  // :1469-1473, results untouched
     if (dbLength <= 0) return 0;
@@ -80,7 +204,7 @@ static int search_into_results(DeviceDb* ddb, const unsigned char* query, int qu
     const auto t0 = now();
     DeviceDb* owned = nullptr;
     if (!ddb && (anyWork || searchType == OPAL_SEARCH_ALIGNMENT)) {
-        ddb = owned = DeviceDb::create(db, dbLength, dbSeqLengths, default_device());
+        ddb = owned = DeviceDb::create(db, dbLength, dbSeqLengths, device);
         if (!ddb) return OPAL_ERR_NO_SIMD_SUPPORT;
     }
     const auto t1 = now();
@@ -134,8 +258,24 @@ int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db
                        const int searchType, int mode, int overflowMethod) {
     DeviceGuard guard;
     (void)overflowMethod;  // OPAL_OVERFLOW_SIMPLE / _BUCKETS only schedule the reference's passes; results are equal
-    return search_into_results(nullptr, query, queryLength, db, dbLength, dbSeqLengths, gapOpen, gapExt, scoreMatrix,
-                               alphabetLength, results, searchType, mode);
+    const std::vector<int> devices = env_devices();
+    const int parts = (int)std::min<size_t>(devices.size(), (size_t)std::max(dbLength / 2, 1));
+    if (parts <= 1 || (mode != OPAL_MODE_NW && mode != OPAL_MODE_HW && mode != OPAL_MODE_OV && mode != OPAL_MODE_SW))
+        return search_into_results(nullptr, query, queryLength, db, dbLength, dbSeqLengths, gapOpen, gapExt, scoreMatrix,
+                                   alphabetLength, results, searchType, mode, devices[0]);
+    // One call = the whole database (reference src/opal.h:150-154), on every listed device: each searches the shard
+    // dealt to it and fills the caller's records of that shard; the alignment stage stays on the owning device.
+    std::vector<std::vector<int>> index;
+    deal_shards(dbSeqLengths, dbLength, parts, &index);
+    return on_shards(parts, [&](int s) -> int {
+        const std::vector<int>& idx = index[s];
+        std::vector<unsigned char*> ptr(idx.size());
+        std::vector<int> len(idx.size());
+        std::vector<OpalSearchResult*> res(idx.size());
+        for (size_t k = 0; k < idx.size(); k++) { ptr[k] = db[idx[k]]; len[k] = dbSeqLengths[idx[k]]; res[k] = results[idx[k]]; }
+        return search_into_results(nullptr, query, queryLength, ptr.data(), (int)idx.size(), len.data(), gapOpen, gapExt, scoreMatrix,
+                                   alphabetLength, res.data(), searchType, mode, devices[s]);
+    });
 }
 
 int opalSearchDatabaseRescore(unsigned char query[], int queryLength, unsigned char* db[], int dbLength, int dbSeqLengths[],
@@ -156,7 +296,7 @@ int opalSearchDatabaseCharSW(unsigned char query[], int queryLength, unsigned ch
     std::vector<int> sc(dbLength, -1);
     int rc = argsFit ? 0 : OPAL_ERR_OVERFLOW;
     if (argsFit) {
-        DeviceDb* ddb = DeviceDb::create(db, dbLength, dbSeqLengths, default_device());
+        DeviceDb* ddb = DeviceDb::create(db, dbLength, dbSeqLengths, env_devices()[0]);
         if (!ddb) return OPAL_ERR_NO_SIMD_SUPPORT;
         const int st = ddb->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, 0, OPAL_MODE_SW, nullptr,
                                    sc.data(), nullptr, nullptr, nullptr);
@@ -192,93 +332,207 @@ void opalb200_trim_cache(void) {
 
 OpalB200Db* opalb200_db_create(unsigned char* db[], int dbLength, const int dbSeqLengths[], int device) {
     DeviceGuard guard;
-    return reinterpret_cast<OpalB200Db*>(DeviceDb::create(db, dbLength, dbSeqLengths, device));
+    if (dbLength < 0 || (dbLength > 0 && (!db || !dbSeqLengths))) { set_error("invalid database"); return nullptr; }
+    const std::vector<int> devices = device >= 0 ? std::vector<int>(1, device) : env_devices();
+    return reinterpret_cast<OpalB200Db*>(create_handle(db, dbLength, dbSeqLengths, devices));
+}
+
+OpalB200Db* opalb200_db_create_multi(unsigned char* db[], int dbLength, const int dbSeqLengths[], const int devices[], int numDevices) {
+    DeviceGuard guard;
+    if (dbLength < 0 || (dbLength > 0 && (!db || !dbSeqLengths))) { set_error("invalid database"); return nullptr; }
+    std::vector<int> devs;
+    for (int k = 0; devices && k < numDevices; k++) devs.push_back(devices[k]);  // an ordinal may repeat (several shards on one device)
+    if (devs.empty()) devs = env_devices();
+    return reinterpret_cast<OpalB200Db*>(create_handle(db, dbLength, dbSeqLengths, devs));
 }
 
 OpalB200Db* opalb200_db_create_sorted(const unsigned char* residues, const int sortedLengths[], const int order[], int dbLength,
                                       int device) {
     DeviceGuard guard;
     if (dbLength < 0 || (dbLength > 0 && (!residues || !sortedLengths))) { set_error("invalid packed database"); return nullptr; }
-    return reinterpret_cast<OpalB200Db*>(DeviceDb::create_sorted(residues, sortedLengths, order, dbLength, device));
+    const std::vector<int> devices = device >= 0 ? std::vector<int>(1, device) : env_devices();
+    if (devices.size() == 1) {
+        DeviceDb* d = DeviceDb::create_sorted(residues, sortedLengths, order, dbLength, devices[0]);
+        if (!d) return nullptr;
+        DbHandle* h = new DbHandle();
+        h->shards.push_back(d); h->n = dbLength; h->residues = d->residues();
+        return reinterpret_cast<OpalB200Db*>(h);
+    }
+    // several devices: the packed sequences are dealt like scattered ones (pointers into the packed buffer)
+    std::vector<unsigned char*> ptr((size_t)dbLength);
+    size_t off = 0;
+    for (int p = 0; p < dbLength; p++) {
+        if (sortedLengths[p] < 0 || (p > 0 && sortedLengths[p] > sortedLengths[p - 1])) { set_error("packed database is not sorted longest first"); return nullptr; }
+        ptr[p] = const_cast<unsigned char*>(residues) + off;
+        off += (size_t)sortedLengths[p];
+    }
+    if (order) {  // must be a permutation of 0..n-1
+        std::vector<char> seen((size_t)std::max(dbLength, 1), 0);
+        for (int p = 0; p < dbLength; p++) {
+            if (order[p] < 0 || order[p] >= dbLength || seen[order[p]]) { set_error("packed database: order[] is not a permutation"); return nullptr; }
+            seen[order[p]] = 1;
+        }
+    }
+    return reinterpret_cast<OpalB200Db*>(create_handle(ptr.data(), dbLength, sortedLengths, devices, order));
 }
 
 void opalb200_db_destroy(OpalB200Db* h) {
     DeviceGuard guard;
-    delete reinterpret_cast<DeviceDb*>(h);
+    delete reinterpret_cast<DbHandle*>(h);
 }
 
-int opalb200_db_length(const OpalB200Db* h) { return reinterpret_cast<const DeviceDb*>(h)->size(); }
+int opalb200_db_length(const OpalB200Db* h) { return reinterpret_cast<const DbHandle*>(h)->n; }
 
-long long opalb200_db_residues(const OpalB200Db* h) { return reinterpret_cast<const DeviceDb*>(h)->residues(); }
+long long opalb200_db_residues(const OpalB200Db* h) { return reinterpret_cast<const DbHandle*>(h)->residues; }
 
-int opalb200_db_search(OpalB200Db* h, const unsigned char query[], int queryLength, int gapOpen, int gapExt,
+int opalb200_db_devices(const OpalB200Db* h) { return reinterpret_cast<const DbHandle*>(h)->parts(); }
+
+int opalb200_db_search(OpalB200Db* hh, const unsigned char query[], int queryLength, int gapOpen, int gapExt,
                        const int* scoreMatrix, int alphabetLength, int searchType, int mode, const unsigned char* skip,
                        int* scores, int* endQuery, int* endTarget, float* deviceMs) {
-    if (!h || !scores) return OPAL_ERR_NO_SIMD_SUPPORT;
+    if (!hh || !scores) return OPAL_ERR_NO_SIMD_SUPPORT;
     DeviceGuard guard;
+    DbHandle* h = reinterpret_cast<DbHandle*>(hh);
     const int wantEnd = searchType != OPAL_SEARCH_SCORE && endQuery && endTarget;
-    return reinterpret_cast<DeviceDb*>(h)->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd,
-                                                  mode, skip, scores, endQuery, endTarget, deviceMs);
+    if (h->index.empty()) {
+        const int rc = h->shards[0]->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd, mode, skip, scores,
+                                            endQuery, endTarget, deviceMs);
+        h->collect_stats();
+        return rc;
+    }
+    std::vector<float> ms((size_t)h->parts(), 0.f);
+    const int rc = on_shards(h->parts(), [&](int s) -> int {
+        const std::vector<int>& idx = h->index[s];
+        const size_t m = idx.size();
+        std::vector<int> sc(m), eq(m, -1), et(m, -1);
+        std::vector<unsigned char> sk;
+        if (skip) { sk.resize(m); for (size_t k = 0; k < m; k++) sk[k] = skip[idx[k]]; }
+        const int r = h->shards[s]->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd, mode,
+                                           skip ? sk.data() : nullptr, sc.data(), eq.data(), et.data(), &ms[s]);
+        if (r) return r;
+        for (size_t k = 0; k < m; k++) {
+            if (skip && sk[k]) continue;
+            scores[idx[k]] = sc[k];
+            if (endQuery) endQuery[idx[k]] = eq[k];
+            if (endTarget) endTarget[idx[k]] = et[k];
+        }
+        return 0;
+    });
+    if (deviceMs) *deviceMs = *std::max_element(ms.begin(), ms.end());  // the devices run concurrently
+    h->collect_stats();
+    return rc;
 }
 
-int opalb200_db_search_batch(OpalB200Db* h, int numQueries, const unsigned char* const queries[], const int queryLengths[],
+int opalb200_db_search_batch(OpalB200Db* hh, int numQueries, const unsigned char* const queries[], const int queryLengths[],
                              int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength, int searchType, int mode,
                              int* scores, int* endQuery, int* endTarget, int inFlight, float* batchMs) {
-    if (!h || !scores || (numQueries > 0 && (!queries || !queryLengths))) return OPAL_ERR_NO_SIMD_SUPPORT;
+    if (!hh || !scores || (numQueries > 0 && (!queries || !queryLengths))) return OPAL_ERR_NO_SIMD_SUPPORT;
     DeviceGuard guard;
+    DbHandle* h = reinterpret_cast<DbHandle*>(hh);
     const int wantEnd = searchType != OPAL_SEARCH_SCORE && endQuery && endTarget;
-    return reinterpret_cast<DeviceDb*>(h)->search_batch(numQueries, queries, queryLengths, gapOpen, gapExt, scoreMatrix,
-                                                        alphabetLength, wantEnd, mode, scores, endQuery, endTarget,
-                                                        inFlight <= 0 ? 3 : inFlight, batchMs);
+    const int fl = inFlight <= 0 ? 3 : inFlight;
+    if (h->index.empty()) {
+        const int rc = h->shards[0]->search_batch(numQueries, queries, queryLengths, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd,
+                                                  mode, scores, endQuery, endTarget, fl, batchMs);
+        h->collect_stats();
+        return rc;
+    }
+    std::vector<float> ms((size_t)h->parts(), 0.f);
+    const size_t n = (size_t)h->n;
+    const int rc = on_shards(h->parts(), [&](int s) -> int {
+        const std::vector<int>& idx = h->index[s];
+        const size_t m = idx.size(), all = m * (size_t)std::max(numQueries, 0);
+        std::vector<int> sc(all), eq(wantEnd ? all : 0), et(wantEnd ? all : 0);
+        const int r = h->shards[s]->search_batch(numQueries, queries, queryLengths, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd,
+                                                 mode, sc.data(), wantEnd ? eq.data() : nullptr, wantEnd ? et.data() : nullptr, fl, &ms[s]);
+        if (r) return r;
+        for (int q = 0; q < numQueries; q++)
+            for (size_t k = 0; k < m; k++) {
+                const size_t to = (size_t)q * n + (size_t)idx[k], from = (size_t)q * m + k;
+                scores[to] = sc[from];
+                if (endQuery) endQuery[to] = wantEnd ? eq[from] : -1;
+                if (endTarget) endTarget[to] = wantEnd ? et[from] : -1;
+            }
+        return 0;
+    });
+    if (batchMs) *batchMs = *std::max_element(ms.begin(), ms.end());
+    h->collect_stats();
+    return rc;
 }
 
-int opalb200_db_search_results(OpalB200Db* h, const unsigned char query[], int queryLength, int gapOpen, int gapExt,
+int opalb200_db_search_results(OpalB200Db* hh, const unsigned char query[], int queryLength, int gapOpen, int gapExt,
                                const int* scoreMatrix, int alphabetLength, OpalSearchResult* results[], int searchType, int mode) {
-    if (!h || !results) return OPAL_ERR_NO_SIMD_SUPPORT;
+    if (!hh || !results) return OPAL_ERR_NO_SIMD_SUPPORT;
     DeviceGuard guard;
-    DeviceDb* ddb = reinterpret_cast<DeviceDb*>(h);
-    return search_into_results(ddb, query, queryLength, nullptr, ddb->size(), nullptr, gapOpen, gapExt, scoreMatrix, alphabetLength,
-                               results, searchType, mode);
+    DbHandle* h = reinterpret_cast<DbHandle*>(hh);
+    if (h->index.empty())
+        return search_into_results(h->shards[0], query, queryLength, nullptr, h->n, nullptr, gapOpen, gapExt, scoreMatrix, alphabetLength,
+                                   results, searchType, mode, h->shards[0]->device());
+    if (mode != OPAL_MODE_NW && mode != OPAL_MODE_HW && mode != OPAL_MODE_OV && mode != OPAL_MODE_SW) return OPAL_ERR_INVALID_MODE;
+    return on_shards(h->parts(), [&](int s) -> int {
+        const std::vector<int>& idx = h->index[s];
+        std::vector<OpalSearchResult*> res(idx.size());
+        for (size_t k = 0; k < idx.size(); k++) res[k] = results[idx[k]];
+        return search_into_results(h->shards[s], query, queryLength, nullptr, (int)idx.size(), nullptr, gapOpen, gapExt, scoreMatrix,
+                                   alphabetLength, res.data(), searchType, mode, h->shards[s]->device());
+    });
 }
 
-int opalb200_db_search_topk(OpalB200Db* h, const unsigned char query[], int queryLength, int gapOpen, int gapExt,
+int opalb200_db_search_topk(OpalB200Db* hh, const unsigned char query[], int queryLength, int gapOpen, int gapExt,
                             const int* scoreMatrix, int alphabetLength, int searchType, int mode, int k, int* indices,
                             OpalSearchResult* results[], int* found) {
     if (found) *found = 0;
-    if (!h || !indices || !results || k < 0) return OPAL_ERR_NO_SIMD_SUPPORT;
+    if (!hh || !indices || !results || k < 0) return OPAL_ERR_NO_SIMD_SUPPORT;
     DeviceGuard guard;
-    DeviceDb* ddb = reinterpret_cast<DeviceDb*>(h);
-    const int n = ddb->size(), kk = std::min(k, n);
-    std::vector<int> sc((size_t)n), eq((size_t)n, -1), et((size_t)n, -1);
+    DbHandle* h = reinterpret_cast<DbHandle*>(hh);
+    const int n = h->n, kk = std::min(k, n), parts = h->parts();
     const int wantEnd = searchType != OPAL_SEARCH_SCORE;
-    int status = ddb->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd, mode, nullptr, sc.data(),
-                             eq.data(), et.data(), nullptr);
+    // Every shard searches and selects ITS k best on the device (DeviceDb::search_topk: only k records per shard come
+    // back, not every score); the candidates are merged here: score descending, caller index ascending among equals.
+    struct Hit { int score, index, endQ, endT, shard, local; };
+    std::vector<std::vector<Hit>> perShard((size_t)parts);
+    int status = on_shards(parts, [&](int s) -> int {
+        const int m = h->shards[s]->size(), ks = std::min(kk, m);
+        std::vector<int> li((size_t)ks), sc((size_t)ks), eq((size_t)ks), et((size_t)ks);
+        const int* map = h->index.empty() ? nullptr : h->index[s].data();
+        const int r = h->shards[s]->search_topk(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd, mode, ks, map,
+                                                li.data(), sc.data(), eq.data(), et.data());
+        if (r) return r;
+        for (int j = 0; j < ks; j++) perShard[s].push_back({sc[j], h->caller_index(s, li[j]), eq[j], et[j], s, li[j]});
+        return 0;
+    });
+    h->collect_stats();
     if (status) return status;
-    // the k best: score descending, caller index ascending among equals
-    std::vector<int> idx((size_t)n);
-    for (int i = 0; i < n; i++) idx[i] = i;
-    auto better = [&](int a, int b) { return sc[a] != sc[b] ? sc[a] > sc[b] : a < b; };
-    if (kk < n) std::nth_element(idx.begin(), idx.begin() + kk, idx.end(), better);
-    std::sort(idx.begin(), idx.begin() + kk, better);
+    std::vector<Hit> hits;
+    for (auto& v : perShard) hits.insert(hits.end(), v.begin(), v.end());
+    auto better = [](const Hit& a, const Hit& b) { return a.score != b.score ? a.score > b.score : a.index < b.index; };
+    std::sort(hits.begin(), hits.end(), better);
+    hits.resize((size_t)kk);
     for (int j = 0; j < kk; j++) {
-        const int i = idx[j];
-        indices[j] = i;
+        indices[j] = hits[j].index;
         opalInitSearchResult(results[j]);
-        opalSearchResultSetScore(results[j], sc[i]);
-        results[j]->endLocationQuery = wantEnd ? eq[i] : -1;
-        results[j]->endLocationTarget = wantEnd ? et[i] : -1;
+        opalSearchResultSetScore(results[j], hits[j].score);
+        results[j]->endLocationQuery = wantEnd ? hits[j].endQ : -1;
+        results[j]->endLocationTarget = wantEnd ? hits[j].endT : -1;
         results[j]->alignmentLength = -1;  // as opalSearchDatabase leaves it below OPAL_SEARCH_ALIGNMENT (:1508-1515)
     }
     if (found) *found = kk;
-    if (searchType == OPAL_SEARCH_ALIGNMENT && kk > 0)
-        status = align_database(ddb, query, queryLength, nullptr, kk, nullptr, gapOpen, gapExt, scoreMatrix, alphabetLength, results,
-                                mode, indices);
+    if (searchType == OPAL_SEARCH_ALIGNMENT && kk > 0)  // start + alignment on the device that owns the target
+        status = on_shards(parts, [&](int s) -> int {
+            std::vector<int> subset;
+            std::vector<OpalSearchResult*> res;
+            for (int j = 0; j < kk; j++)
+                if (hits[j].shard == s) { subset.push_back(hits[j].local); res.push_back(results[j]); }
+            if (subset.empty()) return 0;
+            return align_database(h->shards[s], query, queryLength, nullptr, (int)subset.size(), nullptr, gapOpen, gapExt, scoreMatrix,
+                                  alphabetLength, res.data(), mode, subset.data());
+        });
     return status;
 }
 
 void opalb200_db_last_stats(const OpalB200Db* h, int* kernelLaunches, int* rerun32, int* G, int* R, int* passes,
                             int* warpsPerPartition, int* groups) {
-    const SearchStats& s = reinterpret_cast<const DeviceDb*>(h)->stats();
+    const SearchStats& s = reinterpret_cast<const DbHandle*>(h)->stats;
     if (kernelLaunches) *kernelLaunches = s.kernelLaunches;
     if (rerun32) *rerun32 = s.rerun32;
     if (G) *G = s.G;
@@ -288,7 +542,7 @@ void opalb200_db_last_stats(const OpalB200Db* h, int* kernelLaunches, int* rerun
     if (groups) *groups = s.groups;
 }
 
-int opalb200_db_last_folded(const OpalB200Db* h) { return reinterpret_cast<const DeviceDb*>(h)->stats().foldedTasks; }
+int opalb200_db_last_folded(const OpalB200Db* h) { return reinterpret_cast<const DbHandle*>(h)->stats.foldedTasks; }
 
 double opalb200_measure_dpx_peak(int device, double* threadInstrPerSec, float* ms) {
     DeviceGuard guard;

@@ -423,6 +423,7 @@ static int max_warps_per_partition(int mode, int R, int lanes) {
     return (lanes == 1 && mode != kModeSW) ? launch_bound_for(kFlavorGlobal, R) / 128 : 3;
 }
 
+static inline bool isSWmode(int mode) { return mode == kModeSW; }
 static thread_local int t_forceK = 0, t_forceG = 0, t_forceR = 0;  // development override (OPAL_B200_SPLIT): geometry of the bulk group
 // Several searches in flight (search_batch): the tail of one search overlaps the bulk of the next, so a plan is priced
 // mostly by the SM time it takes, not by when its last task ends.  Measured on BASELINE configs[1], 32 queries with
@@ -1074,6 +1075,11 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
         p.overflowLimit = type == 0 ? 32767 - std::max(maxScore, 0) - 1 : (1 << 30);
         p.padLetterScore = type == 0 ? -16384 : 0;
         p.one = 1; p.keyScale = 1 << kRowBits; p.fastEndLimit = fastEndLimit;
+        {   // range tracking of the 16-bit NW / HW / OV sweeps (see DeviceDb::search for the limits)
+            const long long margin = (long long)(g.R + 3) * ((long long)Go + Ge + absScore_);
+            p.rangeHi = rangeTracking_ ? (int)(32767 - margin) : INT_MAX;   // (not tracking: routed by the a-priori bound)
+            p.rangeLo = rangeTracking_ ? (int)((mode == kModeNW ? -28000 : -16383) + margin) : INT_MIN;
+        }
         void* args[] = {&p};
         const int warpsPerBlock = 4 * g.warpsPerPartition;  // one block per SM, k warps per scheduler partition
         const long long warpsNeeded = ((long long)grp.tasks.size() * g.G + 31) / 32;
@@ -1204,12 +1210,26 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
         const long long hi = (maxP > 0 ? (long long)std::min(Q, T) * maxP : 0) + Go + absP;
         return lo <= lim && hi <= lim;
     };
-    // HW / OV track the last query row in EVERY column a pair sweeps, the pad columns of its shorter member
-    // included.  A pad cell is max(diag + padLetterScore, E, F) with padLetterScore = -16384 at 16 bits, and DPX adds
-    // wrap: diag must stay above -16384 or the cell turns into a large positive "score" of the shorter target.  A pair
-    // is never split between the classes (below), so bounding every member by 16383 bounds the longer one, whose
-    // length the pad columns run to.  NW reads one cell per target (pad columns come after it) and keeps 28000.
-    const long long lim16 = mode == kModeNW ? 28000 : 16383;
+    // NW / HW / OV at 16 bits.  An a-priori bound on every H of a (Q, T) problem -- min(Q, T) maxP upwards,
+    // (Q + T) gapExt downwards -- is hopelessly pessimistic for real sequences (it sends every target beyond ~1,500
+    // residues to the 32-bit class once Q >= 1,500 with BLOSUM62), so only the values that are CERTAIN to occur are
+    // bounded here: the borders of the matrix (column -1: -Go - r Ge for NW and HW; row -1: -Go - c Ge for NW).
+    // Everything else is watched by the kernel (range tracking in search_kernel.cuh: samples of H that stay
+    // (R + 3) D inside the range prove that no cell left it) and a target whose samples come near the limits is
+    // flagged and re-run at 32 bits, exactly like an SW target whose score outgrows 16 bits.
+    // Lower limit: -28000 for NW (the -infinity of E and F sits at -30000).  HW / OV track the last query row in EVERY
+    // column a pair sweeps, the pad columns of its shorter member included, and a pad cell is diag + padLetterScore
+    // (-16384) -- diag must stay above -16383 or the cell wraps into a large positive "score" (ADVICE r1): -16383.
+    const long long D = (long long)Go + Ge + absP;           // bound on the difference of neighbouring cells
+    const long long rangeLoBase = mode == kModeNW ? -28000 : -16383;
+    const long long marginMax = 40 * D;                      // (R + 3) D for the tallest strip (R = 33), rounded up
+    const bool track16 = !isSWmode(mode) && args16 && marginMax <= 6000;
+    auto fits16 = [&](int T) -> bool {
+        const long long border = (long long)Go + (mode == kModeNW ? (long long)std::max(Q, T) : mode == kModeHW ? (long long)Q : 0LL) * Ge;
+        return -border >= rangeLoBase + marginMax;
+    };
+    absScore_ = (int)std::min<long long>(absP, 1 << 28);
+    rangeTracking_ = track16;
     std::vector<int> list16, list32;
     (args16 ? list16 : list32).reserve((size_t)n_);
     bool touched = false;
@@ -1233,7 +1253,7 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
             else if ((maxP > 0 ? (long long)std::min(Q, T) * maxP : 0) < (1LL << 30)) list32.push_back(p);
             else return OPAL_B200_ERR_OVERFLOW;
         } else {
-            if (args16 && fits(T, lim16)) list16.push_back(p);
+            if (track16 ? fits16(T) : (args16 && fits(T, 16000))) list16.push_back(p);  // (second form: penalties too large to track)
             else if (fits(T, 1LL << 30)) list32.push_back(p);
             else return OPAL_B200_ERR_OVERFLOW;
         }
@@ -1318,9 +1338,10 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
             if (rc) return rc != OPAL_B200_ERR_CUDA;  // a CUDA failure has set the error text; other codes pass through
             CUDA_TRY(cudaEventRecord(evStop_, stream_));
             if (!fetch()) return false;
+            // the ladder: what 16 bits could not hold (SW: the score; NW / HW / OV: the range tracking) goes to 32
             std::vector<int> again;
-            publish(list16, isSW ? &again : nullptr);
-            if (!isSW) publish(list32, nullptr);
+            publish(list16, &again);
+            if (!isSW) { publish(list32, nullptr); list32.clear(); }
             if (!again.empty()) {
                 stats_.rerun32 = (int)again.size();
                 std::vector<int> merged(list32.size() + again.size());
@@ -1328,7 +1349,7 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
                 list32.swap(merged);
             }
         }
-        if (isSW && !list32.empty()) {
+        if (!list32.empty()) {
             std::vector<std::pair<int, const std::vector<int>*>> second = {{1, &list32}};
             rc = run_classes(second, dQuery, dMatrix, Q, Go, Ge, A, wantEnd, mode, maxP, &slot);
             if (rc) return rc != OPAL_B200_ERR_CUDA;  // a CUDA failure has set the error text; other codes pass through
@@ -1343,6 +1364,24 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
     const bool okb = body();
     if (!okb) return OPAL_B200_ERR_CUDA;
     return rc;
+}
+
+int DeviceDb::search_topk(const unsigned char* query, int Q, int Go, int Ge, const int* matrix, int A, int wantEnd, int mode, int k,
+                          const int* map, int* outIndex, int* outScore, int* outEndQ, int* outEndT) {
+    const int kk = std::min(k, n_);
+    std::vector<int> sc((size_t)n_), eq((size_t)n_, -1), et((size_t)n_, -1);
+    const int rc = search(query, Q, Go, Ge, matrix, A, wantEnd, mode, nullptr, sc.data(), eq.data(), et.data(), nullptr);
+    if (rc) return rc;
+    std::vector<int> idx((size_t)n_);
+    for (int i = 0; i < n_; i++) idx[i] = i;
+    auto better = [&](int a, int b) { return sc[a] != sc[b] ? sc[a] > sc[b] : (map ? map[a] < map[b] : a < b); };
+    if (kk < n_) std::nth_element(idx.begin(), idx.begin() + kk, idx.end(), better);
+    std::sort(idx.begin(), idx.begin() + kk, better);
+    for (int j = 0; j < kk; j++) {
+        outIndex[j] = idx[j]; outScore[j] = sc[idx[j]];
+        outEndQ[j] = wantEnd ? eq[idx[j]] : -1; outEndT[j] = wantEnd ? et[idx[j]] : -1;
+    }
+    return 0;
 }
 
 int DeviceDb::search_batch(int numQueries, const unsigned char* const* queries, const int* queryLengths, int Go, int Ge,

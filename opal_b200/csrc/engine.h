@@ -67,6 +67,11 @@ public:
     int search(const unsigned char* query, int Q, int Go, int Ge, const int* matrix, int A, int wantEnd, int mode,
                const unsigned char* skip, int* scores, int* endQ, int* endT, float* deviceMs);
 
+    // Score [+ end] search followed by the selection of the k best targets: score descending, then smallest
+    // map[caller index] (map NULL: the caller index itself).  Writes k (<= size()) caller indices and their records.
+    int search_topk(const unsigned char* query, int Q, int Go, int Ge, const int* matrix, int A, int wantEnd, int mode, int k,
+                    const int* map, int* outIndex, int* outScore, int* outEndQ, int* outEndT);
+
     int size() const { return n_; }
     long long residues() const { return totalResidues_; }
     const SearchStats& stats() const { return stats_; }
@@ -124,6 +129,8 @@ private:
     std::vector<cudaEvent_t> auxEvents_;
     SearchStats stats_;
     bool startRecorded_ = false;
+    int absScore_ = 0;            // largest |score matrix entry| of the search in progress
+    bool rangeTracking_ = false;  // its 16-bit NW / HW / OV class is guarded by the kernel's range tracking
 };
 
 double measure_dpx_peak(int device, int mix, double* threadInstrPerSec, float* ms);  // mix 0 = SW recurrence, 1 = NW / HW / OV

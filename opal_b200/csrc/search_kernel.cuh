@@ -105,6 +105,9 @@ struct SearchParams {
     // sorted-target indices; pairStream / pairOffsets then point at the folded stream, whose entry c of a
     // target is (res[c] + 1) | (res[c - 32] + 1) << 8 over T + 32 columns, padded like a pair.
     int folded;
+    // NW / HW / OV at 16 bits: H of every strip's last row is sampled in every column; a target whose samples leave
+    // [rangeLo, rangeHi] is flagged and re-run at 32 bits (see range tracking in the sweep).
+    int rangeHi, rangeLo;
 };
 constexpr int kFoldLag = 32;  // columns between the two halves of a folded task = depth of one warp's wavefront
 
@@ -217,6 +220,7 @@ struct Packed16 {
     static __device__ __forceinline__ reg addmax(reg a, reg b, reg c) { return __viaddmax_s16x2(a, b, c); }
     static __device__ __forceinline__ reg addmax_relu(reg a, reg b, reg c) { return __viaddmax_s16x2_relu(a, b, c); }
     static __device__ __forceinline__ reg vmax(reg a, reg b) { return __vmaxs2(a, b); }
+    static __device__ __forceinline__ reg vmin(reg a, reg b) { return __vmins2(a, b); }
     static __device__ __forceinline__ reg vmax3(reg a, reg b, reg c) { return __vimax3_s16x2(a, b, c); }
     static __device__ __forceinline__ reg add(reg a, reg b) { return __vadd2(a, b); }
     static __device__ __forceinline__ reg bmax(reg a, reg b, bool* phi, bool* plo) { return vibmax_s16x2(a, b, phi, plo); }
@@ -235,6 +239,7 @@ struct Scalar32 {
     static __device__ __forceinline__ reg addmax(reg a, reg b, reg c) { return __viaddmax_s32(a, b, c); }
     static __device__ __forceinline__ reg addmax_relu(reg a, reg b, reg c) { return __viaddmax_s32_relu(a, b, c); }
     static __device__ __forceinline__ reg vmax(reg a, reg b) { return max(a, b); }
+    static __device__ __forceinline__ reg vmin(reg a, reg b) { return min(a, b); }
     static __device__ __forceinline__ reg vmax3(reg a, reg b, reg c) { return __vimax3_s32(a, b, c); }
     static __device__ __forceinline__ reg add(reg a, reg b) { return a + b; }
     static __device__ __forceinline__ reg bmax(reg a, reg b, bool* phi, bool* plo) { *phi = true; return __vibmax_s32(a, b, plo); }
@@ -399,6 +404,14 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         int rowLo, rowHi, colLo, colHi;          // SW end / HW-OV last-row column
         uint32_t keyLo, keyHi;                   // kFlavorSWEndFast: `best` as it was when the half-word last improved
         int nwScore[2], lcScore[2], lcRow[2];    // NW final cell; OV last column
+        // Range tracking (NW / HW / OV, 16 bits).  DPX adds wrap, and unlike SW these modes have no running maximum
+        // that would notice: instead H - Go of the strip's LAST row is sampled in every column (two instructions per
+        // column, not per cell).  Neighbouring cells differ by at most D = gapOpen + gapExt + max |score| in any
+        // direction, so while every sample stays (R + 3) D inside the representable range no cell of the strip -- nor
+        // of the next column -- can have left it; the first sample that does not flags the target for the 32-bit
+        // class, as the reference's short pass hands over to its int pass (src/opal.cpp:802-813, 1000-1017).
+        constexpr bool kRange = FLAVOR == kFlavorGlobal && LANES == 2;
+        reg hiTrack, loTrack;
         const reg* bH = reinterpret_cast<const reg*>(p.bndInH) + off0;  // boundary rows of the previous pass
         const reg* bF = reinterpret_cast<const reg*>(p.bndInF) + off0;
         reg* oH = reinterpret_cast<reg*>(p.bndOutH) + off0;  // ... and of this pass
@@ -420,6 +433,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             keyLo = keyHi = 0;
             nwScore[0] = nwScore[1] = lcScore[0] = lcScore[1] = kScoreNone;
             lcRow[0] = lcRow[1] = -1;
+            hiTrack = TR::splat(TR::NEG); loTrack = TR::splat(32767);
             nextBH = synIdle; nextBF = synIdle;
             if (!firstPass && t == 0 && Tmax > 0) { nextBH = bH[0]; nextBF = bF[0]; }
         };
@@ -575,6 +589,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                 }
                 const reg u = HG[R - 1];
                 outH = u; outF = f;
+                if constexpr (kRange) { hiTrack = TR::vmax(hiTrack, u); loTrack = TR::vmin(loTrack, u); }
 
                 if (TRACK == kFlavorSWEnd) {
                     const reg ch = best ^ bestBefore;
@@ -645,6 +660,8 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                                 }
                                 diag = (diag & lo) | ((uint32_t)TR::splat(border_h(mode, myRow0 + foldRows - 1, Go, Ge) - Go) & hi);
                                 best = (best & lo) | ((uint32_t)TR::splat(TR::NEG) & hi);
+                                hiTrack = (hiTrack & lo) | ((uint32_t)TR::splat(TR::NEG) & hi);  // samples of the idle columns are dropped
+                                loTrack = (loTrack & lo) | ((uint32_t)TR::splat(32767) & hi);
                                 colHi = -1;
                             }
                         }
@@ -662,7 +679,17 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
 
         // ---- reduce the group's candidates (key: score desc, target index asc, query index asc)
         int fsc[2], fcc[2], frr[2];
+        bool outOfRange[2] = {false, false};
         auto reduce = [&](bool keyTracking) {
+            if constexpr (kRange) {  // did any thread's samples leave the safe range?  (bit l = half-word l)
+                unsigned bad = 0;
+#pragma unroll
+                for (int l = 0; l < LANES; l++)
+                    if (TR::lane(hiTrack, l) + Go > p.rangeHi || TR::lane(loTrack, l) + Go < p.rangeLo) bad |= 1u << l;
+                for (int o = 1; o < G; o <<= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+                if (folded) bad = bad ? 3u : 0u;  // one target in both half-words
+                outOfRange[0] = bad & 1u; outOfRange[1] = (bad >> 1) & 1u;
+            }
 #pragma unroll
             for (int l = 0; l < LANES; l++) {
                 int sc = kScoreNone, cc = 0x7fffffff, rr = 0x7fffffff;  // this thread's candidate
@@ -731,7 +758,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             if (t == 0 && tgt[l] >= 0) {
                 const int i = tgt[l];
                 int sc = fsc[l], cc = fcc[l], rr = frr[l];
-                bool overflow = (kSW && sc > p.overflowLimit) || pairInexact;
+                bool overflow = (kSW && sc > p.overflowLimit) || pairInexact || outOfRange[l];
                 if (!firstPass) {
                     const int ps0 = p.outScore[i];
                     if (ps0 == kScoreOverflow) overflow = true;

@@ -28,6 +28,10 @@ class OpalB200(OpalCLibrary):
         L.opalb200_last_error.restype = ctypes.c_char_p
         L.opalb200_db_create.argtypes = [vp, ci, vp, ci]
         L.opalb200_db_create.restype = vp
+        L.opalb200_db_create_multi.argtypes = [vp, ci, vp, vp, ci]
+        L.opalb200_db_create_multi.restype = vp
+        L.opalb200_db_devices.argtypes = [vp]
+        L.opalb200_db_devices.restype = ci
         L.opalb200_db_create_sorted.argtypes = [vp, vp, vp, ci, ci]
         L.opalb200_db_create_sorted.restype = vp
         L.opalb200_db_search_batch.argtypes = [vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, vp, vp, vp, ci, vp]
@@ -62,7 +66,12 @@ class OpalB200(OpalCLibrary):
         return self.lib.opalb200_last_error().decode()
 
     def create_db(self, db: SequenceDB, device=0):
-        h = self.lib.opalb200_db_create(db.pointers.ctypes.data, len(db), db.lengths.ctypes.data, int(device))
+        """opalb200_db_create on one device, or -- `device` a list of ordinals -- opalb200_db_create_multi."""
+        if isinstance(device, (list, tuple)):
+            devs = np.ascontiguousarray(device, dtype=np.int32)
+            h = self.lib.opalb200_db_create_multi(db.pointers.ctypes.data, len(db), db.lengths.ctypes.data, devs.ctypes.data, int(devs.size))
+        else:
+            h = self.lib.opalb200_db_create(db.pointers.ctypes.data, len(db), db.lengths.ctypes.data, int(device))
         if not h:
             raise RuntimeError("opalb200_db_create failed: " + self.last_error())
         return ResidentDb(self, h, len(db))
@@ -169,6 +178,9 @@ class ResidentDb:
             self.handle, qbuf.ctypes.data, int(query.size), int(gap_open), int(gap_ext), sm.ctypes.data,
             int(alphabet_length), int(search_type), int(mode), int(k), idx.ctypes.data, rp.ctypes.data, ctypes.byref(found))
         return rc, idx[:found.value], results[:found.value]
+
+    def devices(self):
+        return int(self.eng.lib.opalb200_db_devices(self.handle))
 
     def last_stats(self):
         v = [ctypes.c_int(0) for _ in range(7)]

@@ -157,3 +157,33 @@ def test_char_sw_and_invalid_mode(product):
     rc, res = product.search_database(README_QUERY, db, 3, 1, README_MATRIX, 4, res, 0, 7, OPAL_OVERFLOW_SIMPLE)
     assert rc == 3
     assert dump_results(res) == g["invalid_mode"]["results"]
+
+
+@pytest.mark.parametrize("mode", ["NW", "HW", "OV"])
+def test_range_tracking_flags_scores_that_leave_16_bits(product, oracle, mode):
+    """NW / HW / OV at 16 bits are guarded by sampled range tracking instead of an a-priori bound: targets whose cells
+    come near the ends of the 16-bit range -- upwards (scaled matrix, near-identical sequences) or downwards (a long
+    query against short targets, very long gaps) -- must be re-run at 32 bits, everything else stays at 16."""
+    rng = np.random.default_rng(12)
+    sm = matrices.blosum62()
+    # upwards: 6 x BLOSUM62 on a 1,300-residue query and copies of it (true scores up to ~45,000)
+    q = datasets.random_residues(1300, rng, sm)
+    seqs = [datasets.random_residues(int(n), rng, sm) for n in rng.integers(50, 900, 30)]
+    seqs[0] = q.copy()
+    seqs[1] = datasets.mutate(q, 0.97, rng, sm)
+    seqs[2] = q[:700].copy()                       # ~24,000: inside 16 bits but near enough to the limit region
+    seqs[3] = datasets.mutate(q, 0.6, rng, sm)
+    m6 = (sm.matrix * 6).ravel()
+    db = SequenceDB.from_sequences(seqs)
+    rc, want = search_dump(oracle, q, db, 66, 6, m6, 23, 1, MODES[mode])
+    assert rc == 0 and max(r[1] for r in want) > 32767
+    _compare(product, oracle, q, db, 66, 6, m6, 23, modes=(mode,))
+    # downwards: queries of 12,000 ... 27,000 against short targets (NW / HW scores around -Q) and unequal pairs
+    for qlen in (12000, 16300, 21000, 27000):
+        ql = datasets.random_residues(qlen, rng, sm)
+        seqs = [datasets.random_residues(int(n), rng, sm) for n in (700, 650, 300, 299, 90, 40, 5, 1)]
+        _compare(product, oracle, ql, SequenceDB.from_sequences(seqs), 11, 1, sm.flat(), 23, modes=(mode,), types=(1,))
+    # long targets against a short query: NW's first row runs down to -T
+    qs = datasets.random_residues(200, rng, sm)
+    seqs = [datasets.random_residues(int(n), rng, sm) for n in (27500, 26000, 16500, 16000, 9000, 8999, 120)]
+    _compare(product, oracle, qs, SequenceDB.from_sequences(seqs), 11, 1, sm.flat(), 23, modes=(mode,), types=(1,))
