@@ -82,7 +82,7 @@ int opalb200_db_search(OpalB200Db* handle, const unsigned char query[], int quer
 
 /*
  * numQueries searches against the resident database (config 3's protocol: many queries, one database), with up
- * to `inFlight` (1..8) queries on the device at a time so that the tail of one query overlaps the bulk of the
+ * to `inFlight` (1..16) queries on the device at a time so that the tail of one query overlaps the bulk of the
  * next and host-side planning / result publishing overlaps kernels.  Same arguments as opalb200_db_search;
  * outputs are numQueries x dbLength ints, row q = query q, in caller order.  batchMs (nullable) receives the
  * CUDA-event time from the start of the batch to the last kernel end.
@@ -91,6 +91,15 @@ int opalb200_db_search_batch(OpalB200Db* handle, int numQueries, const unsigned 
                              const int queryLengths[], int gapOpen, int gapExt, const int* scoreMatrix,
                              int alphabetLength, int searchType, int mode,
                              int* scores, int* endQuery, int* endTarget, int inFlight, float* batchMs);
+
+/*
+ * The same with a mode per search (modes[s] = OPAL_MODE_*): the reference's performance protocol loops modes x queries
+ * over one database (test/perf:15-24); in one batch the tail of the last search of a mode overlaps the first of the next.
+ */
+int opalb200_db_search_batch_modes(OpalB200Db* handle, int numSearches, const unsigned char* const queries[],
+                                   const int queryLengths[], const int modes[], int gapOpen, int gapExt,
+                                   const int* scoreMatrix, int alphabetLength, int searchType,
+                                   int* scores, int* endQuery, int* endTarget, int inFlight, float* batchMs);
 
 /*
  * opalSearchDatabase (reference src/opal.h:150-154) against the resident database: same result records, same

@@ -138,6 +138,8 @@ static DbHandle* create_handle(unsigned char* const* db, int n, const int* lens,
         return h;
     }
     deal_shards(lens, n, parts, &h->index);
+    if (callerIndex)  // keep every shard in ascending CALLER index (ties between equal scores are broken by it, on the device too)
+        for (auto& v : h->index) std::sort(v.begin(), v.end(), [&](int a, int b) { return callerIndex[a] < callerIndex[b]; });
     const int rc = on_shards(parts, [&](int s) -> int {
         const std::vector<int>& idx = h->index[s];
         std::vector<unsigned char*> ptr(idx.size());
@@ -423,9 +425,31 @@ int opalb200_db_search(OpalB200Db* hh, const unsigned char query[], int queryLen
     return rc;
 }
 
+static int search_batch_modes(OpalB200Db* hh, int numQueries, const unsigned char* const queries[], const int queryLengths[],
+                              int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength, int searchType, int mode,
+                              const int* modes, int* scores, int* endQuery, int* endTarget, int inFlight, float* batchMs);
+
 int opalb200_db_search_batch(OpalB200Db* hh, int numQueries, const unsigned char* const queries[], const int queryLengths[],
                              int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength, int searchType, int mode,
                              int* scores, int* endQuery, int* endTarget, int inFlight, float* batchMs) {
+    return search_batch_modes(hh, numQueries, queries, queryLengths, gapOpen, gapExt, scoreMatrix, alphabetLength, searchType, mode,
+                              nullptr, scores, endQuery, endTarget, inFlight, batchMs);
+}
+
+int opalb200_db_search_batch_modes(OpalB200Db* hh, int numSearches, const unsigned char* const queries[], const int queryLengths[],
+                                   const int modes[], int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength,
+                                   int searchType, int* scores, int* endQuery, int* endTarget, int inFlight, float* batchMs) {
+    if (numSearches > 0 && !modes) return OPAL_ERR_INVALID_MODE;
+    for (int q = 0; q < numSearches; q++)
+        if (modes[q] != OPAL_MODE_NW && modes[q] != OPAL_MODE_HW && modes[q] != OPAL_MODE_OV && modes[q] != OPAL_MODE_SW)
+            return OPAL_ERR_INVALID_MODE;
+    return search_batch_modes(hh, numSearches, queries, queryLengths, gapOpen, gapExt, scoreMatrix, alphabetLength, searchType,
+                              OPAL_MODE_SW, modes, scores, endQuery, endTarget, inFlight, batchMs);
+}
+
+static int search_batch_modes(OpalB200Db* hh, int numQueries, const unsigned char* const queries[], const int queryLengths[],
+                              int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength, int searchType, int mode,
+                              const int* modes, int* scores, int* endQuery, int* endTarget, int inFlight, float* batchMs) {
     if (!hh || !scores || (numQueries > 0 && (!queries || !queryLengths))) return OPAL_ERR_NO_SIMD_SUPPORT;
     DeviceGuard guard;
     DbHandle* h = reinterpret_cast<DbHandle*>(hh);
@@ -433,7 +457,7 @@ int opalb200_db_search_batch(OpalB200Db* hh, int numQueries, const unsigned char
     const int fl = inFlight <= 0 ? 3 : inFlight;
     if (h->index.empty()) {
         const int rc = h->shards[0]->search_batch(numQueries, queries, queryLengths, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd,
-                                                  mode, scores, endQuery, endTarget, fl, batchMs);
+                                                  mode, scores, endQuery, endTarget, fl, batchMs, modes);
         h->collect_stats();
         return rc;
     }
@@ -444,7 +468,7 @@ int opalb200_db_search_batch(OpalB200Db* hh, int numQueries, const unsigned char
         const size_t m = idx.size(), all = m * (size_t)std::max(numQueries, 0);
         std::vector<int> sc(all), eq(wantEnd ? all : 0), et(wantEnd ? all : 0);
         const int r = h->shards[s]->search_batch(numQueries, queries, queryLengths, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd,
-                                                 mode, sc.data(), wantEnd ? eq.data() : nullptr, wantEnd ? et.data() : nullptr, fl, &ms[s]);
+                                                 mode, sc.data(), wantEnd ? eq.data() : nullptr, wantEnd ? et.data() : nullptr, fl, &ms[s], modes);
         if (r) return r;
         for (int q = 0; q < numQueries; q++)
             for (size_t k = 0; k < m; k++) {

@@ -618,6 +618,65 @@ static __global__ void pack_folded_kernel(const uint8_t* residues, const long lo
     foldStream[e] = (uint16_t)word;
 }
 
+// ------------------------------------------------------------------ device-side selection (search_topk)
+// Sorted positions in [0, to) whose 16-bit result is "re-run me" (or missing): the ladder's hand-over list, gathered on
+// the device so that only the list travels to the host, not every score.
+static __global__ void collect_flagged_kernel(const int* score, int to, int* outList, int* outCount) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < to; p += gridDim.x * blockDim.x) {
+        const int sc = score[p];
+        if (sc == kScoreOverflow || sc == kScoreNone) outList[atomicAdd(outCount, 1)] = p;
+    }
+}
+
+// Zero-length targets (the tail of the length-sorted order) get their defined result without a sweep.
+static __global__ void fill_empty_kernel(int* score, int* endQ, int* endT, int from, int to, int sc, int eq, int et) {
+    for (int p = from + blockIdx.x * blockDim.x + threadIdx.x; p < to; p += gridDim.x * blockDim.x) { score[p] = sc; endQ[p] = eq; endT[p] = et; }
+}
+
+// The k best of n results under the key (score descending, caller index ascending): radix select over the 64-bit key
+// (score biased to unsigned | ~caller index) -- eight passes of one 1024-thread block, a 256-bin shared-memory
+// histogram each, narrow the k-th largest key down byte by byte (keys are unique, so exactly k results lie at or above
+// it); a ninth pass writes those k records {caller index, score, endQ, endT}, unordered.  All of it reads the score
+// array where the search kernels left it: 8 n bytes per pass out of L2.
+__device__ __forceinline__ unsigned long long topk_key(int score, int callerIndex) {
+    return ((unsigned long long)((unsigned)score ^ 0x80000000u) << 32) | (unsigned long long)(0xffffffffu - (unsigned)callerIndex);
+}
+static __global__ void __launch_bounds__(1024) topk_select_kernel(const int* score, const int* endQ, const int* endT, const int* order,
+                                                                  int n, int k, int wantEnd, int4* records) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned long long prefix;  // the bytes of the k-th largest key decided so far (high bytes)
+    __shared__ unsigned remaining, written;
+    if (threadIdx.x == 0) { prefix = 0; remaining = (unsigned)k; written = 0; }
+    for (int byte = 7; byte >= 0; byte--) {
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const unsigned long long pre = prefix;
+        const int shift = 8 * byte;
+        for (int p = threadIdx.x; p < n; p += blockDim.x) {
+            const unsigned long long key = topk_key(score[p], order[p]);
+            if (byte == 7 || (key >> (shift + 8)) == pre) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned need = remaining, b = 255;
+            for (;; b--) {  // buckets from the top: the one that holds the k-th largest key
+                if (hist[b] >= need || b == 0) break;
+                need -= hist[b];
+            }
+            remaining = need;
+            prefix = (pre << 8) | b;
+        }
+        __syncthreads();
+    }
+    const unsigned long long threshold = prefix;
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        if (topk_key(score[p], order[p]) >= threshold) {
+            const unsigned slot = atomicAdd(&written, 1u);
+            if (slot < (unsigned)k) records[slot] = make_int4(order[p], score[p], wantEnd ? endQ[p] : 0x7fffffff, wantEnd ? endT[p] : 0x7fffffff);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ DeviceDb
 DeviceDb* DeviceDb::create(unsigned char* const* db, int n, const int* lens, int device) {
     return build(db, nullptr, lens, nullptr, n, device);
@@ -644,6 +703,8 @@ bool DeviceDb::alloc_search_buffers() {
     // a single copy.
     const size_t nWords = (size_t)std::max(n_, 1);
     if (!device_alloc(device_, (void**)&dResults_, sizeof(int) * 5 * nWords)) return false;
+    // (the copy back covers entries no kernel writes -- skipped and zero-length targets, never read by the host)
+    CUDA_TRY(cudaMemsetAsync(dResults_, 0xff, sizeof(int) * 3 * nWords, stream_));
     if (!pinned_alloc((void**)&hResults_, sizeof(int) * 3 * nWords)) return false;
     dScore_ = dResults_; dEndQ_ = dResults_ + nWords; dEndT_ = dResults_ + 2 * nWords; dTaskList_ = dResults_ + 3 * nWords;
     hScore_ = hResults_; hEndQ_ = hResults_ + nWords; hEndT_ = hResults_ + 2 * nWords;
@@ -895,7 +956,7 @@ DeviceDb::~DeviceDb() {
     void* own[] = {dResults_, dArgs_, dBndH_, dBndF_};
     for (void* p : own) device_release(device_, p);
     if (ownsDb_) {
-        void* shared[] = {dBlock_, dPairStream_, dFoldStream_};
+        void* shared[] = {dBlock_, dPairStream_, dFoldStream_, dOrder_};
         for (void* p : shared) device_release(device_, p);
         pinned_release(hBlock_); pinned_release(hMaxCode_);
     }
@@ -983,7 +1044,12 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
                     double tL = 0, tB = 0;
                     if (!pick_geometry(Q, A, lanes, variant ? tlFold : tl, 0, tasksL, smemLimit_, smL, mode, true, flavorClass, &gL, &tL, variant != 0)) continue;
                     if (!pick_geometry(Q, A, lanes, tl, m, nT, smemLimit_, numSMs_ - smL, mode, false, flavorClass, &gB, &tB)) continue;
-                    const double t = std::max(tL, tB) + 3000.0;  // a second launch is not free
+                    // One search alone ends when its slower group ends.  With searches overlapping (search_batch) the SMs a
+                    // group leaves are taken by the next search, so a plan costs the SM time it holds: the latency class
+                    // then shrinks to the fewest SMs its tasks fit on instead of the fewest that end them soonest (measured
+                    // on an eighth of BASELINE configs[2]: up to eight searches in flight each held 4+ SMs at a third of
+                    // their issue rate for a tail several times longer than its bulk).
+                    const double t = (t_overlapped ? (smL * tL + (numSMs_ - smL) * tB) / numSMs_ : std::max(tL, tB)) + 3000.0;  // a second launch is not free
                     if (t < bestT * 0.97) { bestT = t; bestM = m; bestSm = smL; bestL = gL; bestB = gB; }
                 }
             }
@@ -1073,7 +1139,11 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
         p.bndOutH = dBndH_ ? dBndH_ + (pass & 1) * half : nullptr; p.bndOutF = dBndF_ ? dBndF_ + (pass & 1) * half : nullptr;
         p.outScore = dScore_; p.outEndQ = dEndQ_; p.outEndT = dEndT_;
         p.overflowLimit = type == 0 ? 32767 - std::max(maxScore, 0) - 1 : (1 << 30);
-        p.padLetterScore = type == 0 ? -16384 : 0;
+        // The "no residue" letter of the 16-bit streams (pad columns of a pair's shorter member, idle columns).  SW: a
+        // pad cell must not raise the running maximum; HW / OV: the last query row is tracked in pad columns too and
+        // must stay below what the real columns gave -- very negative.  NW reads one cell per target and never a pad
+        // column: 0 keeps pad cells inside the range of the real ones, so they cannot trip the range tracking.
+        p.padLetterScore = type == 0 ? (mode == kModeNW ? 0 : -16384) : 0;
         p.one = 1; p.keyScale = 1 << kRowBits; p.fastEndLimit = fastEndLimit;
         {   // range tracking of the 16-bit NW / HW / OV sweeps (see DeviceDb::search for the limits)
             const long long margin = (long long)(g.R + 3) * ((long long)Go + Ge + absScore_);
@@ -1233,10 +1303,12 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
     std::vector<int> list16, list32;
     (args16 ? list16 : list32).reserve((size_t)n_);
     bool touched = false;
+    int emptyFrom = n_;  // keepOnDevice_: first sorted position of the zero-length targets
     for (int p = 0; p < n_; p++) {
         const int i = order_[p];
         if (skip && skip[i]) continue;
         const int T = sortedLen_[p];
+        if (T == 0 && keepOnDevice_) { emptyFrom = std::min(emptyFrom, p); continue; }  // filled on the device (search_topk)
         if (T == 0 || Q <= 0) {  // nothing to align: defined as in oracle/opal_oracle.c
             int sc = 0, eq = Q - 1, et = T - 1;
             if (Q > 0 && (mode == kModeNW || mode == kModeHW)) sc = -Go - (Q - 1) * Ge;  // the query against one gap
@@ -1258,7 +1330,7 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
             else return OPAL_B200_ERR_OVERFLOW;
         }
     }
-    if (!touched) return 0;
+    if (!touched && !keepOnDevice_) return 0;
     trace.mark("route");
     // The 16-bit class works on whole pairs (sorted targets 2p, 2p+1) and the two classes of NW/HW/OV run
     // concurrently, so a pair is never split between them: if one member needs 32 bits, both go there.
@@ -1328,6 +1400,25 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
             });
             if (overflowed) std::sort(overflowed->begin(), overflowed->end());
         };
+        // search_topk: results stay on the device; the hand-over list of the ladder is gathered there (a count and the
+        // flagged positions come back instead of every score)
+        auto collect = [&](std::vector<int>* flagged) -> bool {
+            flagged->clear();
+            if (emptyFrom <= 0) return true;
+            CUDA_TRY(cudaMemsetAsync(dSelect_, 0, sizeof(int), stream_));
+            collect_flagged_kernel<<<std::min(numSMs_ * 4, (emptyFrom + 255) / 256), 256, 0, stream_>>>(dScore_, emptyFrom, dSelect_ + 1, dSelect_);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(hResults_, dSelect_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+            CUDA_TRY(cudaStreamSynchronize(stream_));
+            const int count = hResults_[0];
+            if (count > 0) {
+                CUDA_TRY(cudaMemcpyAsync(hResults_, dSelect_ + 1, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, stream_));
+                CUDA_TRY(cudaStreamSynchronize(stream_));
+                flagged->assign(hResults_, hResults_ + count);
+                std::sort(flagged->begin(), flagged->end());
+            }
+            return true;
+        };
         // NW/HW/OV classes are independent (routed a priori) and run concurrently; SW's 32-bit class is the
         // re-run of what overflowed 16 bits and has to follow it.
         std::vector<std::pair<int, const std::vector<int>*>> first;
@@ -1337,11 +1428,16 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
             rc = run_classes(first, dQuery, dMatrix, Q, Go, Ge, A, wantEnd, mode, maxP, &slot);
             if (rc) return rc != OPAL_B200_ERR_CUDA;  // a CUDA failure has set the error text; other codes pass through
             CUDA_TRY(cudaEventRecord(evStop_, stream_));
-            if (!fetch()) return false;
             // the ladder: what 16 bits could not hold (SW: the score; NW / HW / OV: the range tracking) goes to 32
             std::vector<int> again;
-            publish(list16, &again);
-            if (!isSW) { publish(list32, nullptr); list32.clear(); }
+            if (keepOnDevice_) {
+                if (!collect(&again)) return false;
+                if (!isSW) list32.clear();
+            } else {
+                if (!fetch()) return false;
+                publish(list16, &again);
+                if (!isSW) { publish(list32, nullptr); list32.clear(); }
+            }
             if (!again.empty()) {
                 stats_.rerun32 = (int)again.size();
                 std::vector<int> merged(list32.size() + again.size());
@@ -1354,8 +1450,21 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
             rc = run_classes(second, dQuery, dMatrix, Q, Go, Ge, A, wantEnd, mode, maxP, &slot);
             if (rc) return rc != OPAL_B200_ERR_CUDA;  // a CUDA failure has set the error text; other codes pass through
             CUDA_TRY(cudaEventRecord(evStop_, stream_));
-            if (!fetch()) return false;
-            publish(list32, nullptr);
+            if (keepOnDevice_) {
+                std::vector<int> still;
+                if (!collect(&still)) return false;
+                if (!still.empty()) rc = OPAL_B200_ERR_OVERFLOW;
+            } else {
+                if (!fetch()) return false;
+                publish(list32, nullptr);
+            }
+        }
+        if (keepOnDevice_ && emptyFrom < n_) {  // zero-length targets: the defined result, written where a sweep would have left it
+            int sc = 0, eq = Q - 1, et = -1;
+            if (mode == kModeNW || mode == kModeHW) sc = -Go - (Q - 1) * Ge;
+            if (isSW) { eq = 0x7fffffff; et = 0x7fffffff; }
+            fill_empty_kernel<<<std::min(numSMs_, (n_ - emptyFrom + 255) / 256), 256, 0, stream_>>>(dScore_, dEndQ_, dEndT_, emptyFrom, n_, sc, eq, et);
+            CUDA_TRY(cudaGetLastError());
         }
         trace.mark("publish");
         if (deviceMs && startRecorded_) CUDA_TRY(cudaEventElapsedTime(deviceMs, evStart_, evStop_));
@@ -1369,27 +1478,58 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
 int DeviceDb::search_topk(const unsigned char* query, int Q, int Go, int Ge, const int* matrix, int A, int wantEnd, int mode, int k,
                           const int* map, int* outIndex, int* outScore, int* outEndQ, int* outEndT) {
     const int kk = std::min(k, n_);
-    std::vector<int> sc((size_t)n_), eq((size_t)n_, -1), et((size_t)n_, -1);
-    const int rc = search(query, Q, Go, Ge, matrix, A, wantEnd, mode, nullptr, sc.data(), eq.data(), et.data(), nullptr);
-    if (rc) return rc;
-    std::vector<int> idx((size_t)n_);
-    for (int i = 0; i < n_; i++) idx[i] = i;
-    auto better = [&](int a, int b) { return sc[a] != sc[b] ? sc[a] > sc[b] : (map ? map[a] < map[b] : a < b); };
-    if (kk < n_) std::nth_element(idx.begin(), idx.begin() + kk, idx.end(), better);
-    std::sort(idx.begin(), idx.begin() + kk, better);
+    if (kk <= 0) return 0;
+    if (Q <= 0) {  // degenerate: every result is written by the host anyway
+        std::vector<int> sc((size_t)n_), eq((size_t)n_, -1), et((size_t)n_, -1);
+        const int rc = search(query, Q, Go, Ge, matrix, A, wantEnd, mode, nullptr, sc.data(), eq.data(), et.data(), nullptr);
+        if (rc) return rc;
+        std::vector<int> idx((size_t)n_);
+        for (int i = 0; i < n_; i++) idx[i] = i;
+        auto better = [&](int a, int b) { return sc[a] != sc[b] ? sc[a] > sc[b] : (map ? map[a] < map[b] : a < b); };
+        std::partial_sort(idx.begin(), idx.begin() + kk, idx.end(), better);
+        for (int j = 0; j < kk; j++) { outIndex[j] = idx[j]; outScore[j] = sc[idx[j]]; outEndQ[j] = wantEnd ? eq[idx[j]] : -1; outEndT[j] = wantEnd ? et[idx[j]] : -1; }
+        return 0;
+    }
+    // Device path: the search leaves [score | endQ | endT] in HBM, the k best are selected there (caller indices of a
+    // shard ascend with the map, so the key can use them) and 16 k bytes come back.
+    if (cudaSetDevice(device_) != cudaSuccess) { set_error("cudaSetDevice failed"); return OPAL_B200_ERR_CUDA; }
+    const size_t selectInts = (size_t)n_ + 4 * (size_t)kk + 16;
+    if (!device_alloc(device_, (void**)&dSelect_, sizeof(int) * selectInts)) return OPAL_B200_ERR_CUDA;
+    auto release = [&]() { device_release(device_, dSelect_); dSelect_ = nullptr; keepOnDevice_ = false; };
+    if (!dOrder_) {
+        if (!ensure_uploaded() || !device_alloc(device_, (void**)&dOrder_, sizeof(int) * (size_t)std::max(n_, 1)) ||
+            cudaMemcpyAsync(dOrder_, order_.data(), sizeof(int) * (size_t)n_, cudaMemcpyHostToDevice, stream_) != cudaSuccess ||
+            cudaStreamSynchronize(stream_) != cudaSuccess) {
+            set_error("upload of the index map failed"); release(); return OPAL_B200_ERR_CUDA;
+        }
+    }
+    keepOnDevice_ = true;
+    const int rc = search(query, Q, Go, Ge, matrix, A, wantEnd, mode, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc) { release(); return rc; }
+    int4* dRecords = reinterpret_cast<int4*>(dSelect_ + (((size_t)n_ + 4) & ~(size_t)3));
+    topk_select_kernel<<<1, 1024, 0, stream_>>>(dScore_, dEndQ_, dEndT_, dOrder_, n_, kk, wantEnd, dRecords);
+    std::vector<int4> rec((size_t)kk);
+    if (cudaGetLastError() != cudaSuccess ||
+        cudaMemcpyAsync(rec.data(), dRecords, sizeof(int4) * (size_t)kk, cudaMemcpyDeviceToHost, stream_) != cudaSuccess ||
+        cudaStreamSynchronize(stream_) != cudaSuccess) {
+        set_error("top-k selection failed"); release(); return OPAL_B200_ERR_CUDA;
+    }
+    release();
+    std::sort(rec.begin(), rec.end(), [&](const int4& a, const int4& b) { return a.y != b.y ? a.y > b.y : (map ? map[a.x] < map[b.x] : a.x < b.x); });
     for (int j = 0; j < kk; j++) {
-        outIndex[j] = idx[j]; outScore[j] = sc[idx[j]];
-        outEndQ[j] = wantEnd ? eq[idx[j]] : -1; outEndT[j] = wantEnd ? et[idx[j]] : -1;
+        outIndex[j] = rec[j].x; outScore[j] = rec[j].y;
+        outEndQ[j] = (wantEnd && rec[j].z != 0x7fffffff) ? rec[j].z : -1;
+        outEndT[j] = (wantEnd && rec[j].w != 0x7fffffff) ? rec[j].w : -1;
     }
     return 0;
 }
 
 int DeviceDb::search_batch(int numQueries, const unsigned char* const* queries, const int* queryLengths, int Go, int Ge,
                            const int* matrix, int A, int wantEnd, int mode, int* scores, int* endQ, int* endT, int inFlight,
-                           float* batchMs) {
+                           float* batchMs, const int* modes) {
     if (batchMs) *batchMs = 0.f;
     if (numQueries <= 0) return 0;
-    const int K = std::max(1, std::min(std::min(inFlight, numQueries), 8));
+    const int K = std::max(1, std::min(std::min(inFlight, numQueries), 16));
     if (cudaSetDevice(device_) != cudaSuccess) { set_error("cudaSetDevice failed"); return OPAL_B200_ERR_CUDA; }
     while ((int)contexts_.size() < K - 1) {
         DeviceDb* c = clone_context();
@@ -1411,7 +1551,7 @@ int DeviceDb::search_batch(int numQueries, const unsigned char* const* queries, 
             const int q = next.fetch_add(1);
             if (q >= numQueries) break;
             const size_t base = (size_t)q * (size_t)n_;
-            const int rc = ctx->search(queries[q], queryLengths[q], Go, Ge, matrix, A, wantEnd, mode, nullptr, scores + base,
+            const int rc = ctx->search(queries[q], queryLengths[q], Go, Ge, matrix, A, wantEnd, modes ? modes[q] : mode, nullptr, scores + base,
                                        endQ ? endQ + base : nullptr, endT ? endT + base : nullptr, nullptr);
             if (rc) { rcs[k] = rc; errors[k] = last_error(); break; }
             launches[k] += ctx->stats_.kernelLaunches; reruns[k] += ctx->stats_.rerun32;

@@ -59,7 +59,7 @@ public:
     // bulk of the next and host-side planning / publishing overlaps kernels.  Outputs are [query][caller index].
     int search_batch(int numQueries, const unsigned char* const* queries, const int* queryLengths, int Go, int Ge,
                      const int* matrix, int A, int wantEnd, int mode, int* scores, int* endQ, int* endT, int inFlight,
-                     float* batchMs);
+                     float* batchMs, const int* modes = nullptr);  // modes: one per query (NULL: `mode` for all)
     // Blocks until the upload issued by create() has finished (create() returns with it in flight).
     bool ensure_uploaded();
 
@@ -129,6 +129,9 @@ private:
     std::vector<cudaEvent_t> auxEvents_;
     SearchStats stats_;
     bool startRecorded_ = false;
+    bool keepOnDevice_ = false;   // search_topk: results stay in HBM, the ladder's hand-over list is gathered there
+    int* dSelect_ = nullptr;      // search_topk scratch: [count | flagged positions (n) | k records]
+    int* dOrder_ = nullptr;       // device copy of order_ (sorted position -> caller index), made by the first search_topk
     int absScore_ = 0;            // largest |score matrix entry| of the search in progress
     bool rangeTracking_ = false;  // its 16-bit NW / HW / OV class is guarded by the kernel's range tracking
 };

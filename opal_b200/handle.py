@@ -36,6 +36,8 @@ class OpalB200(OpalCLibrary):
         L.opalb200_db_create_sorted.restype = vp
         L.opalb200_db_search_batch.argtypes = [vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, vp, vp, vp, ci, vp]
         L.opalb200_db_search_batch.restype = ci
+        L.opalb200_db_search_batch_modes.argtypes = [vp, ci, vp, vp, vp, ci, ci, vp, ci, ci, vp, vp, vp, ci, vp]
+        L.opalb200_db_search_batch_modes.restype = ci
         L.opalb200_db_search_results.argtypes = [vp, vp, ci, ci, ci, vp, ci, vp, ci, ci]
         L.opalb200_db_search_results.restype = ci
         L.opalb200_db_search_topk.argtypes = [vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, vp, vp, ctypes.POINTER(ci)]
@@ -140,6 +142,14 @@ class ResidentDb:
             eq = np.full((nq, self.n), -1, dtype=np.int32)
             et = np.full((nq, self.n), -1, dtype=np.int32)
         ms = ctypes.c_float(0)
+        if isinstance(mode, (list, tuple)):  # one mode per search: opalb200_db_search_batch_modes
+            modes = np.array([MODES[m] if isinstance(m, str) else int(m) for m in mode], dtype=np.int32)
+            assert len(modes) == nq
+            rc = self.eng.lib.opalb200_db_search_batch_modes(
+                self.handle, nq, ptrs.ctypes.data, qlens.ctypes.data, modes.ctypes.data, int(gap_open), int(gap_ext), sm.ctypes.data,
+                int(alphabet_length), int(search_type), sc.ctypes.data, eq.ctypes.data, et.ctypes.data,
+                int(in_flight), ctypes.byref(ms))
+            return rc, sc, eq, et, float(ms.value)
         if isinstance(mode, str):
             mode = MODES[mode]
         rc = self.eng.lib.opalb200_db_search_batch(

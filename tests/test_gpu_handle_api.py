@@ -187,3 +187,34 @@ def test_topk_pipeline_equals_the_two_call_protocol(product, mode):
         assert rc == 0 and len(idx) == 0
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("mode", ["SW", "NW", "HW", "OV"])
+def test_topk_selection_on_the_device_ties_empties_and_reruns(product, mode):
+    """The device-side selection (radix select over score | ~index): tie-heavy scores (tiny alphabet), zero-length
+    targets, targets that are re-run at 32 bits (scaled matrix, copies of the query) and every k from 1 to n."""
+    rng = np.random.default_rng(19)
+    a = 3
+    m = (matrices.simple(a, 2, -1).matrix * 300).ravel().astype(np.int32)
+    q = rng.integers(0, a, 150).astype(np.uint8)
+    seqs = [rng.integers(0, a, int(n)).astype(np.uint8) for n in rng.integers(0, 40, 260)]
+    for i in (3, 17, 101):
+        seqs[i] = np.zeros(0, np.uint8)
+    seqs[50] = q.copy()                                 # score 150 * 600 = 90,000: beyond 16 bits
+    seqs[51] = np.concatenate([q[:100], q[:100]])
+    for i in range(200, 230):
+        seqs[i] = seqs[199].copy()                      # 31 identical targets: equal scores, ordered by index
+    db = SequenceDB.from_sequences(seqs)
+    rc, full = product.search_database(q, db, 900, 300, m, a, None, 1, MODES[mode])
+    assert rc == 0
+    order = sorted(range(len(db)), key=lambda i: (-int(full["score"][i]), i))
+    ref = dump_results(full)
+    h = product.create_db(db, 0)
+    try:
+        for k in (1, 2, 31, 64, 229, len(db) - 1, len(db)):
+            rc, idx, top = h.search_topk(q, 900, 300, m, a, 1, mode, k)
+            assert rc == 0, product.last_error()
+            assert idx.tolist() == order[:k], (mode, k)
+            assert dump_results(top) == [ref[i] for i in order[:k]]
+    finally:
+        h.close()
