@@ -154,7 +154,7 @@ def cpu_sweep(lib, w, shards):
     def work(k):
         for mode in w.modes:
             for q in w.queries:
-                results[k][:] = blank[k]
+                np.copyto(results[k].view(np.uint8), blank[k].view(np.uint8))
                 rc, _ = lib.search_database(q, shards[k], GAP_OPEN, GAP_EXT, sm.flat(), sm.alphabet_length, results[k],
                                             w.search_type, MODES[mode], OPAL_OVERFLOW_BUCKETS)
                 rcs[k] |= rc
@@ -301,11 +301,12 @@ def run_b200_arm(args, rank, local_rank, world):
     # ---- end to end through the drop-in C ABI (host buffers in, OpalSearchResult records out), one call per search
     blank = new_results(n)
     res = blank.copy()
+    res_bytes, blank_bytes = res.view(np.uint8), blank.view(np.uint8)  # flat views: the reset below is one memcpy
 
     def step_e2e():
         for mode in w.modes:
             for q in w.queries:
-                res[:] = blank  # the caller's opalInitSearchResult loop (reference src/opal_aligner.cpp:150-154)
+                np.copyto(res_bytes, blank_bytes)  # the caller's opalInitSearchResult loop (reference src/opal_aligner.cpp:150-154)
                 rc, _ = eng.search_database(q, db, GAP_OPEN, GAP_EXT, mat, A, res, w.search_type, MODES[mode], OPAL_OVERFLOW_BUCKETS)
                 if rc != 0:
                     raise SystemExit(f"opalSearchDatabase failed rc={rc}: {eng.last_error()}")
@@ -327,6 +328,40 @@ def run_b200_arm(args, rank, local_rank, world):
     calls = len(w.modes) * nq
     h2d = int(calls * (index_bytes + db.total_residues + 64 + 1024 + (4 * A * A + 255) // 256 * 256 + 16) + len(w.modes) * w.sum_q)
     d2h = int(calls * (3 * 4 * n + 4))
+
+    # ---- one process, every GPU (N > 1): the same sweep as ONE opalSearchDatabase call per search over the WHOLE database,
+    # dealt over all N devices inside the library (OPAL_B200_DEVICES); rank 0 alone, the other ranks wait on the host
+    one_process = None
+    if world > 1 and not single and not args.no_extras:
+        import datetime
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            full = w.full_db
+            os.environ["OPAL_B200_DEVICES"] = ",".join(str(d) for d in range(world))
+            blank_full = new_results(len(full))
+            res_full = blank_full.copy()
+            rf_bytes, bf_bytes = res_full.view(np.uint8), blank_full.view(np.uint8)
+
+            def sweep_all_devices():
+                for mode in w.modes:
+                    for q in w.queries:
+                        np.copyto(rf_bytes, bf_bytes)
+                        rc, _ = eng.search_database(q, full, GAP_OPEN, GAP_EXT, mat, A, res_full, w.search_type, MODES[mode], OPAL_OVERFLOW_BUCKETS)
+                        if rc != 0:
+                            raise SystemExit(f"opalSearchDatabase on {world} devices failed rc={rc}: {eng.last_error()}")
+
+            sweep_all_devices()
+            t0 = time.perf_counter()
+            sweep_all_devices()
+            dt = time.perf_counter() - t0
+            del os.environ["OPAL_B200_DEVICES"]
+            one_process = {"value": float(w.sum_q) * len(w.modes) * full.total_residues / 1e9 / dt, "unit": "GCUPS", "devices": world,
+                           "ms_per_step": dt * 1e3,
+                           "note": "wall clock, one process: each opalSearchDatabase call packs, uploads and searches the whole database on all "
+                                   "devices (host threads of this process: its 1/N share of the cores, as for the e2e figure)"}
+            store.set("one_process_done", "1")
+        else:
+            store.wait(["one_process_done"], datetime.timedelta(seconds=1800))
 
     # ---- extras (rank 0's shard, untimed region): every (mode, query) alone, score+end and score only; SW beside them
     extras = {}
@@ -389,6 +424,8 @@ def run_b200_arm(args, rank, local_rank, world):
         if args.shard_of > 1:
             line["details"]["emulation"] = f"rank 0's shard of a {args.shard_of}-way deal on one GPU (development run, not a scaling result)"
         line.update(extras)
+        if one_process:
+            line["one_process_multi_gpu"] = one_process
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

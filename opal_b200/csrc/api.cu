@@ -211,26 +211,9 @@ static int search_into_results(DeviceDb* ddb, const unsigned char* query, int qu
     }
     const auto t1 = now();
     int status = 0;
-    if (anyWork) {
-        std::vector<int> sc(dbLength), eq(dbLength, -1), et(dbLength, -1);
-        status = ddb->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd, mode, skip.data(),
-                             sc.data(), eq.data(), et.data(), nullptr);
-        if (status == 0) {
-            parallel_for(dbLength, 65536, [&](long long lo, long long hi) {
-                for (long long i = lo; i < hi; i++) {
-                    if (skip[i]) continue;
-                    opalSearchResultSetScore(results[i], sc[i]);
-                    results[i]->endLocationQuery = wantEnd ? eq[i] : -1;  // :420-426, 869-905
-                    results[i]->endLocationTarget = wantEnd ? et[i] : -1;
-                    if (searchType != OPAL_SEARCH_ALIGNMENT) {  // :1508-1515, same pass
-                        results[i]->alignment = NULL;
-                        results[i]->alignmentLength = -1;
-                        results[i]->startLocationQuery = results[i]->startLocationTarget = -1;
-                    }
-                }
-            });
-        }
-    }
+    if (anyWork)  // results go straight into the records (same pass also sets the no-alignment fields, :1508-1515)
+        status = ddb->search(query, queryLength, gapOpen, gapExt, scoreMatrix, alphabetLength, wantEnd, mode, skip.data(), nullptr,
+                             nullptr, nullptr, nullptr, results, searchType != OPAL_SEARCH_ALIGNMENT);
     const auto t2 = now();
     if (status == 0 && searchType == OPAL_SEARCH_ALIGNMENT)
         status = align_database(ddb, query, queryLength, db, dbLength, dbSeqLengths, gapOpen, gapExt, scoreMatrix, alphabetLength,
@@ -330,6 +313,7 @@ const char* opalb200_last_error(void) { return last_error(); }
 void opalb200_trim_cache(void) {
     DeviceGuard guard;
     trim_cache();
+    trim_layouts();
 }
 
 OpalB200Db* opalb200_db_create(unsigned char* db[], int dbLength, const int dbSeqLengths[], int device) {

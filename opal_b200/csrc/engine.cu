@@ -339,48 +339,74 @@ void parallel_for(long long n, long long grain, const std::function<void(long lo
     pool.run(parts, [&](int k) { body(n * k / parts, n * (k + 1) / parts); }, [](int) {});
 }
 
-// The index vectors of a database (a few MB for half a million sequences) are recycled between databases: a
-// drop-in call builds and drops one per call, and fresh heap memory of that size is page-faulted in every time.
-namespace {
-struct HostArrays { std::vector<int> order, pos, sortedLen; std::vector<long long> offsets, copyOff; };
-std::mutex g_arraysMu;
-std::vector<HostArrays> g_arrays;
-HostArrays take_host_arrays() {
-    std::lock_guard<std::mutex> lk(g_arraysMu);
-    if (g_arrays.empty()) return HostArrays();
-    HostArrays h = std::move(g_arrays.back());
-    g_arrays.pop_back();
-    return h;
+// ------------------------------------------------------------------ layouts
+// Everything about a database that depends only on its sequence LENGTHS -- the length sort, the index maps, the offsets
+// of the plain / paired / folded streams, the planner's prefix sums -- is computed once and remembered, keyed by the
+// length array itself (compared in full: a few MB, ~0.1 ms): the drop-in opalSearchDatabase packs its database on
+// every call, and callers run query after query against the same sequences (reference test/perf:15-24).  The residues
+// are NOT cached: they are staged and uploaded on every call, as the signature demands.
+void TaskLens::build() {
+    for (int sh = 0; sh < 6; sh++) {
+        const size_t g = (size_t)1 << sh, cnt = (len.size() + g - 1) / g;
+        prefix[sh].assign(cnt + 1, 0.0);
+        for (size_t k = 0; k < cnt; k++) prefix[sh][k + 1] = prefix[sh][k] + len[k * g];
+    }
 }
-void give_host_arrays(HostArrays&& h) {
-    std::lock_guard<std::mutex> lk(g_arraysMu);
-    if (g_arrays.size() < 4 && h.order.capacity() <= (64u << 20)) g_arrays.push_back(std::move(h));
+
+const TaskLens& Layout::pair_lens() const {
+    std::call_once(pairOnce_, [this] {
+        const int m = (nonEmpty + 1) / 2;
+        pairLens_.len.resize((size_t)m);
+        for (int k = 0; k < m; k++) pairLens_.len[k] = sortedLen[2 * (size_t)k];
+        pairLens_.build();
+    });
+    return pairLens_;
+}
+const TaskLens& Layout::target_lens() const {
+    std::call_once(targetOnce_, [this] {
+        targetLens_.len.assign(sortedLen.begin(), sortedLen.begin() + nonEmpty);
+        targetLens_.build();
+    });
+    return targetLens_;
+}
+
+namespace {
+std::mutex g_layoutMu;
+std::vector<std::shared_ptr<Layout>> g_layouts;  // most recently used last
+constexpr size_t kMaxLayouts = 12, kMaxLayoutBytes = 384u << 20;
+
+std::shared_ptr<Layout> find_layout(const int* lens, int n) {
+    std::lock_guard<std::mutex> lk(g_layoutMu);
+    for (size_t k = g_layouts.size(); k-- > 0;) {
+        const std::shared_ptr<Layout>& l = g_layouts[k];
+        if ((int)l->lens.size() == n && (n == 0 || memcmp(l->lens.data(), lens, sizeof(int) * (size_t)n) == 0)) {
+            std::shared_ptr<Layout> hit = l;
+            g_layouts.erase(g_layouts.begin() + (long)k);
+            g_layouts.push_back(hit);
+            return hit;
+        }
+    }
+    return nullptr;
+}
+void remember_layout(const std::shared_ptr<Layout>& l) {
+    std::lock_guard<std::mutex> lk(g_layoutMu);
+    g_layouts.push_back(l);
+    size_t bytes = 0;
+    for (const auto& e : g_layouts) bytes += 44 * e->lens.size();
+    while (g_layouts.size() > kMaxLayouts || (bytes > kMaxLayoutBytes && g_layouts.size() > 1)) {
+        bytes -= 44 * g_layouts.front()->lens.size();
+        g_layouts.erase(g_layouts.begin());
+    }
 }
 }  // namespace
+void trim_layouts() {
+    std::lock_guard<std::mutex> lk(g_layoutMu);
+    g_layouts.clear();
+}
 
 // Thread stride in the profile: a multiple of 4 words (16-byte aligned LDS.128) with an odd number of
 // 16-byte units, so the 8 lanes of a quarter-warp hit 8 different bank groups whatever their residues are.
 static int rpad_of(int R) { const int r4 = (R + 3) / 4; return 4 * ((r4 % 2 == 0) ? r4 + 1 : r4); }
-
-// Task lengths of one class (longest first) with strided prefix sums, so that the planner can price any
-// contiguous range of tasks under any group size in O(1).
-struct TaskLens {
-    std::vector<int> len;
-    std::vector<double> prefix[6];  // prefix[s][k] = sum of len[i] over i = 0, g, 2g, ... < k*g with g = 1 << s
-    void build() {
-        for (int sh = 0; sh < 6; sh++) {
-            const size_t g = (size_t)1 << sh, cnt = (len.size() + g - 1) / g;
-            prefix[sh].assign(cnt + 1, 0.0);
-            for (size_t k = 0; k < cnt; k++) prefix[sh][k + 1] = prefix[sh][k] + len[k * g];
-        }
-    }
-    // sum of len[i] for i = lo, lo+g, ... < hi  (lo must be a multiple of g = 1 << sh), and how many terms
-    double strided(int sh, size_t lo, size_t hi, double* terms) const {
-        const size_t g = (size_t)1 << sh, a = lo / g, b = (hi + g - 1) / g;
-        *terms = (double)(b - a);
-        return prefix[sh][b] - prefix[sh][a];
-    }
-};
 
 // Picks (G, R, passes, warps per scheduler partition) for a query of Q rows over `taskLens` (one entry
 // per task, longest first) on `numSMs` SMs, and returns the estimated cycles in *estCycles.
@@ -618,6 +644,91 @@ static __global__ void pack_folded_kernel(const uint8_t* residues, const long lo
     foldStream[e] = (uint16_t)word;
 }
 
+// The layout of a database: found in the cache or built (and, for scattered databases, remembered).  `order` is the
+// caller's permutation of a packed database (NULL: identity); NULL + error text on invalid lengths.
+std::shared_ptr<const Layout> layout_for(const int* lens, const int* order, int n, bool packed, bool* cachedOut) {
+    std::shared_ptr<Layout> lay = packed ? nullptr : find_layout(lens, n);
+    if (cachedOut) *cachedOut = lay != nullptr;
+    if (lay) return lay;
+    lay = std::make_shared<Layout>();
+    Layout& L = *lay;
+    int maxLen = 0;
+    for (int i = 0; i < n; i++) {
+        if (lens[i] < 0) { set_error("negative sequence length"); return nullptr; }
+        maxLen = std::max(maxLen, lens[i]);
+    }
+    L.lens.assign(lens, lens + n);
+    L.order.resize(n);
+    L.pos.resize(n);
+    if (packed) {
+        for (int p = 0; p < n; p++) L.order[p] = order ? order[p] : p;
+    } else if (maxLen <= (1 << 22) && n >= (1 << 17) && (long long)HostPool::get().width() * (maxLen + 2) <= (16LL << 20)) {
+        // large database: counting sort with one histogram per host thread (contiguous index ranges, so the
+        // result is still stable in caller order) -- the scatter is a cache miss per sequence
+        const int W = HostPool::get().width(), B = maxLen + 1;
+        std::vector<int> hist((size_t)W * B, 0);
+        HostPool::get().run(W, [&](int k) {
+            int* h = hist.data() + (size_t)k * B;
+            for (long long i = (long long)n * k / W, e = (long long)n * (k + 1) / W; i < e; i++) h[maxLen - lens[i]]++;
+        }, [](int) {});
+        int at = 0;
+        for (int b = 0; b < B; b++)
+            for (int k = 0; k < W; k++) { const int c = hist[(size_t)k * B + b]; hist[(size_t)k * B + b] = at; at += c; }
+        HostPool::get().run(W, [&](int k) {
+            int* h = hist.data() + (size_t)k * B;
+            for (long long i = (long long)n * k / W, e = (long long)n * (k + 1) / W; i < e; i++) L.order[h[maxLen - lens[i]]++] = (int)i;
+        }, [](int) {});
+    } else if (maxLen <= (1 << 22)) {
+        std::vector<int> start(maxLen + 2, 0);
+        for (int i = 0; i < n; i++) start[maxLen - lens[i] + 1]++;
+        for (int k = 1; k <= maxLen + 1; k++) start[k] += start[k - 1];
+        for (int i = 0; i < n; i++) L.order[start[maxLen - lens[i]]++] = i;
+    } else {
+        for (int i = 0; i < n; i++) L.order[i] = i;
+        std::stable_sort(L.order.begin(), L.order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
+    }
+    // Residues are stored in the order they are copied in -- caller order for scattered sequences (sequential
+    // reads of the caller's memory, runs of adjacent sequences merge into one memcpy), sorted order for a
+    // packed database -- and offsets[p] says where sorted position p lives.  Nothing needs the sorted
+    // sequences to be adjacent: the 16-bit kernels stream the paired layout built on the device below.
+    L.copyOff.resize((size_t)n + 1);
+    long long sum = 0;
+    for (int i = 0; i < n; i++) { L.copyOff[i] = sum; sum += lens[i]; }
+    L.copyOff[n] = sum;
+    L.total = sum;
+    L.sortedLen.resize(n);
+    L.offsets.resize((size_t)n + 1);
+    parallel_for(n, 65536, [&](long long lo, long long hi) {
+        for (long long p = lo; p < hi; p++) {
+            const int i = L.order[p];
+            L.pos[i] = (int)p;
+            L.sortedLen[p] = packed ? lens[p] : lens[i];
+            L.offsets[p] = packed ? L.copyOff[p] : L.copyOff[i];
+        }
+    });
+    L.offsets[n] = sum;
+    L.nonEmpty = n;
+    while (L.nonEmpty > 0 && L.sortedLen[L.nonEmpty - 1] == 0) L.nonEmpty--;
+    // paired stream: [32 zeros][pair 0 columns][32 zeros][pair 1 ...]; the longest targets also get a folded
+    // stream (an even number of them: the bulk keeps whole pairs)
+    L.numPairs = (n + 1) / 2;
+    L.numFold = getenv("OPAL_B200_NO_FOLD") ? 0 : std::min(n & ~1, kFoldTargets);
+    while (L.numFold > 0 && L.sortedLen[L.numFold - 1] < kFoldMinLength) L.numFold -= 2;
+    L.numFold = std::max(L.numFold, 0);
+    L.pairOff.resize((size_t)std::max(L.numPairs, 1));
+    L.foldOff.resize((size_t)std::max(L.numFold, 1));
+    L.entries = 32;
+    L.pairOff[0] = 32;
+    for (int p = 0; p < L.numPairs; p++) { L.pairOff[p] = L.entries; L.entries += L.sortedLen[2 * (size_t)p] + 32; }
+    L.entries += 64;
+    L.foldEntries = 32;
+    L.foldOff[0] = 32;
+    for (int p = 0; p < L.numFold; p++) { L.foldOff[p] = L.foldEntries; L.foldEntries += L.sortedLen[p] + kFoldLag + 32; }
+    L.foldEntries += 64;
+    if (!packed) remember_layout(lay);
+    return lay;
+}
+
 // ------------------------------------------------------------------ device-side selection (search_topk)
 // Sorted positions in [0, to) whose 16-bit result is "re-run me" (or missing): the ladder's hand-over list, gathered on
 // the device so that only the list travels to the host, not every score.
@@ -733,68 +844,16 @@ DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed,
         PhaseTrace trace("build");
         trace.mark("setup");
 
-        // ---- sort by length, longest first (counting sort; stable in caller order)
-        int maxLen = 0;
-        for (int i = 0; i < n; i++) {
-            if (lens[i] < 0) { set_error("negative sequence length"); return false; }
-            maxLen = std::max(maxLen, lens[i]);
-        }
-        {
-            HostArrays h = take_host_arrays();
-            d->order_.swap(h.order); d->pos_.swap(h.pos); d->sortedLen_.swap(h.sortedLen); d->offsets_.swap(h.offsets);
-            d->copyOff_.swap(h.copyOff);
-        }
-        d->order_.resize(n);
-        d->pos_.resize(n);
-        if (packed) {
-            for (int p = 0; p < n; p++) d->order_[p] = order ? order[p] : p;
-        } else if (maxLen <= (1 << 22) && n >= (1 << 17) && (long long)HostPool::get().width() * (maxLen + 2) <= (16LL << 20)) {
-            // large database: the same counting sort with one histogram per host thread (contiguous index ranges,
-            // so the result is still stable in caller order) -- the scatter is a cache miss per sequence
-            const int W = HostPool::get().width(), B = maxLen + 1;
-            std::vector<int> hist((size_t)W * B, 0);
-            HostPool::get().run(W, [&](int k) {
-                int* h = hist.data() + (size_t)k * B;
-                for (long long i = (long long)n * k / W, e = (long long)n * (k + 1) / W; i < e; i++) h[maxLen - lens[i]]++;
-            }, [](int) {});
-            int at = 0;
-            for (int b = 0; b < B; b++)
-                for (int k = 0; k < W; k++) { const int c = hist[(size_t)k * B + b]; hist[(size_t)k * B + b] = at; at += c; }
-            HostPool::get().run(W, [&](int k) {
-                int* h = hist.data() + (size_t)k * B;
-                for (long long i = (long long)n * k / W, e = (long long)n * (k + 1) / W; i < e; i++) d->order_[h[maxLen - lens[i]]++] = (int)i;
-            }, [](int) {});
-        } else if (maxLen <= (1 << 22)) {
-            std::vector<int> start(maxLen + 2, 0);
-            for (int i = 0; i < n; i++) start[maxLen - lens[i] + 1]++;
-            for (int k = 1; k <= maxLen + 1; k++) start[k] += start[k - 1];
-            for (int i = 0; i < n; i++) d->order_[start[maxLen - lens[i]]++] = i;
-        } else {
-            for (int i = 0; i < n; i++) d->order_[i] = i;
-            std::stable_sort(d->order_.begin(), d->order_.end(), [&](int a, int b) { return lens[a] > lens[b]; });
-        }
-        // Residues are stored in the order they are copied in -- caller order for scattered sequences (sequential
-        // reads of the caller's memory, runs of adjacent sequences merge into one memcpy), sorted order for a
-        // packed database -- and offsets_[p] says where sorted position p lives.  Nothing needs the sorted
-        // sequences to be adjacent: the 16-bit kernels stream the paired layout built on the device below.
-        std::vector<long long>& copyOff = d->copyOff_;  // offsets in copy order (scratch of this function, recycled)
-        copyOff.resize((size_t)n + 1);
-        long long total = 0;
-        for (int i = 0; i < n; i++) { copyOff[i] = total; total += lens[i]; }
-        copyOff[n] = total;
-        d->sortedLen_.resize(n);
-        d->offsets_.resize((size_t)n + 1);
-        parallel_for(n, 65536, [&](long long lo, long long hi) {
-            for (long long p = lo; p < hi; p++) {
-                const int i = d->order_[p];
-                d->pos_[i] = (int)p;
-                d->sortedLen_[p] = packed ? lens[p] : lens[i];
-                d->offsets_[p] = packed ? copyOff[p] : copyOff[i];
-            }
-        });
-        d->offsets_[n] = total;
+        // ---- the layout: length sort (longest first, stable in caller order), index maps, stream offsets.  A pure
+        // function of the length array: remembered between calls for scattered databases (see "layouts" above).
+        bool cached = false;
+        std::shared_ptr<const Layout> lay = layout_for(lens, order, n, packed != nullptr, &cached);
+        if (!lay) return false;
+        d->lay_ = lay;
+        const long long total = lay->total;
+        const std::vector<long long>& copyOff = lay->copyOff;
         d->totalResidues_ = total;
-        trace.mark("sort");
+        trace.mark(cached ? "layout (cached)" : "layout");
         if (!d->alloc_search_buffers()) return false;
         trace.mark("buffers");
 
@@ -802,11 +861,8 @@ DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed,
         // operation costs tens of microseconds on its own here, far more than its share of a few MB, so the
         // database goes up in a single copy once the gather is complete.)  The residues part stays as the host
         // copy the alignment stage replays against.  Paired stream: [32 zeros][pair 0 columns][32 zeros][pair 1 ...].
-        d->numPairs_ = (n + 1) / 2;
-        // the longest targets also get a folded stream (an even number of them: the bulk keeps whole pairs)
-        d->numFold_ = getenv("OPAL_B200_NO_FOLD") ? 0 : std::min(n & ~1, kFoldTargets);
-        while (d->numFold_ > 0 && d->sortedLen_[d->numFold_ - 1] < kFoldMinLength) d->numFold_ -= 2;
-        d->numFold_ = std::max(d->numFold_, 0);
+        d->numPairs_ = lay->numPairs;
+        d->numFold_ = lay->numFold;
         const size_t nOff = (size_t)n + 1, nPair = (size_t)std::max(d->numPairs_, 1), nLen = (size_t)std::max(n, 1);
         const size_t nFold = (size_t)std::max(d->numFold_, 1);
         const size_t indexBytes = (sizeof(long long) * (nOff + nPair + nFold) + sizeof(int) * (nLen + 1) + 255) / 256 * 256;
@@ -824,18 +880,13 @@ DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed,
         d->dLengths_ = reinterpret_cast<int*>(d->dFoldOffsets_ + nFold);
         d->dMaxCode_ = d->dLengths_ + nLen;
         d->dResidues_ = d->dBlock_ + indexBytes;
-        memcpy(hOff, d->offsets_.data(), sizeof(long long) * nOff);
+        memcpy(hOff, lay->offsets.data(), sizeof(long long) * nOff);
+        memcpy(hPair, lay->pairOff.data(), sizeof(long long) * nPair);
+        memcpy(hFold, lay->foldOff.data(), sizeof(long long) * nFold);
         hLen[0] = 0;
-        if (n > 0) memcpy(hLen, d->sortedLen_.data(), sizeof(int) * (size_t)n);
+        if (n > 0) memcpy(hLen, lay->sortedLen.data(), sizeof(int) * (size_t)n);
         hLen[nLen] = 0;  // max code, raised by the pairing kernel
-        long long entries = 32;
-        hPair[0] = 32;
-        for (int p = 0; p < d->numPairs_; p++) { hPair[p] = entries; entries += d->sortedLen_[2 * p] + 32; }
-        entries += 64;
-        long long foldEntries = 32;
-        hFold[0] = 32;
-        for (int p = 0; p < d->numFold_; p++) { hFold[p] = foldEntries; foldEntries += d->sortedLen_[p] + kFoldLag + 32; }
-        foldEntries += 64;
+        const long long entries = lay->entries, foldEntries = lay->foldEntries;
         uint8_t* staging = d->hResidues_;
         memset(staging + total, 0, 64);
         // Parts of about equal residue count, cut at sequence boundaries; each is uploaded as soon as it and all
@@ -932,11 +983,7 @@ DeviceDb* DeviceDb::clone_context() {
     DeviceDb* c = new DeviceDb();
     c->ownsDb_ = false; c->uploaded_ = true;
     c->device_ = device_; c->n_ = n_; c->numSMs_ = numSMs_; c->smemLimit_ = smemLimit_; c->totalResidues_ = totalResidues_;
-    {
-        HostArrays h = take_host_arrays();
-        c->order_.swap(h.order); c->pos_.swap(h.pos); c->sortedLen_.swap(h.sortedLen); c->offsets_.swap(h.offsets);
-    }
-    c->order_ = order_; c->pos_ = pos_; c->sortedLen_ = sortedLen_; c->offsets_ = offsets_;
+    c->lay_ = lay_;
     c->hResidues_ = hResidues_; c->dResidues_ = dResidues_; c->dOffsets_ = dOffsets_; c->dLengths_ = dLengths_;
     c->dPairStream_ = dPairStream_; c->dPairOffsets_ = dPairOffsets_; c->numPairs_ = numPairs_; c->maxCode_ = maxCode_;
     c->dFoldStream_ = dFoldStream_; c->dFoldOffsets_ = dFoldOffsets_; c->numFold_ = numFold_;
@@ -945,11 +992,6 @@ DeviceDb* DeviceDb::clone_context() {
 }
 
 DeviceDb::~DeviceDb() {
-    {
-        HostArrays h;
-        h.order.swap(order_); h.pos.swap(pos_); h.sortedLen.swap(sortedLen_); h.offsets.swap(offsets_); h.copyOff.swap(copyOff_);
-        give_host_arrays(std::move(h));
-    }
     cudaSetDevice(device_);
     for (DeviceDb* c : contexts_) delete c;
     if (stream_) cudaStreamSynchronize(stream_);
@@ -999,10 +1041,16 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
     } else {
         tasks = list;
     }
-    TaskLens tl;
-    tl.len.resize(tasks.size());
-    for (size_t k = 0; k < tasks.size(); k++) tl.len[k] = sortedLen_[lanes == 2 ? 2 * tasks[k] : tasks[k]];
-    tl.build();
+    // The usual list is "every non-empty target": its prefix sums live with the layout (they cost more than the rest
+    // of the planning for half a million targets and depend on nothing else).
+    TaskLens own;
+    const bool everything = (int)list.size() == lay_->nonEmpty && list.front() == 0 && list.back() == lay_->nonEmpty - 1;
+    if (!everything) {
+        own.len.resize(tasks.size());
+        for (size_t k = 0; k < tasks.size(); k++) own.len[k] = lay_->sortedLen[lanes == 2 ? 2 * tasks[k] : tasks[k]];
+        own.build();
+    }
+    const TaskLens& tl = everything ? (lanes == 2 ? lay_->pair_lens() : lay_->target_lens()) : own;
     const size_t nT = tasks.size();
 
     Geometry gAll;
@@ -1021,7 +1069,7 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
     size_t foldable = 0;
     if (lanes == 2 && numFold_ > 0 && !getenv("OPAL_B200_NO_FOLD") && (mode == kModeSW || !getenv("OPAL_B200_NO_FOLD_GLOBAL"))) {
         while (foldable < (size_t)numFold_ && foldable < list.size() && list[foldable] == (int)foldable) foldable++;
-        tlFold.len.assign(sortedLen_.begin(), sortedLen_.begin() + foldable);
+        tlFold.len.assign(lay_->sortedLen.begin(), lay_->sortedLen.begin() + foldable);
         tlFold.build();
     }
     if (!getenv("OPAL_B200_NO_SPLIT") && !getenv("OPAL_B200_GEOMETRY")) {
@@ -1203,7 +1251,7 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
         for (const Group& g : groups)
             fprintf(stderr, "[opal-b200] group type=%d%s tasks=%zu longest=%d G=%d R=%d k=%d passes=%d blocks<=%d est=%.0f kcycles\n", g.type,
                     g.g.folded ? " folded" : "", g.tasks.size(),
-                    g.tasks.empty() ? 0 : sortedLen_[g.type == 0 && !g.g.folded ? 2 * g.tasks[0] : g.tasks[0]], g.g.G, g.g.R,
+                    g.tasks.empty() ? 0 : lay_->sortedLen[g.type == 0 && !g.g.folded ? 2 * g.tasks[0] : g.tasks[0]], g.g.G, g.g.R,
                     g.g.warpsPerPartition, g.g.passes, g.maxBlocks, g.estCycles / 1e3);
     bool badArgument = false;
     auto body = [&]() -> bool {
@@ -1240,8 +1288,22 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
 }
 
 int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const int* matrix, int A, int wantEnd, int mode,
-                     const unsigned char* skip, int* scores, int* endQ, int* endT, float* deviceMs) {
+                     const unsigned char* skip, int* scores, int* endQ, int* endT, float* deviceMs,
+                     OpalSearchResult* const* records, bool noAlignmentFill) {
     stats_ = SearchStats();
+    // one result of caller index i (end locations already -1 where there is none)
+    auto emit = [&](int i, int sc, int eq, int et) {
+        if (records) {
+            OpalSearchResult* r = records[i];
+            r->scoreSet = 1; r->score = sc;                                  // reference src/opal.cpp:1561-1564
+            r->endLocationQuery = eq; r->endLocationTarget = et;              // :420-426, 869-905
+            if (noAlignmentFill) { r->alignment = NULL; r->alignmentLength = -1; r->startLocationQuery = r->startLocationTarget = -1; }
+        } else {
+            scores[i] = sc;
+            if (endQ) endQ[i] = eq;
+            if (endT) endT[i] = et;
+        }
+    };
     PhaseTrace trace("search");
     if (deviceMs) *deviceMs = 0.f;
     if (mode != kModeNW && mode != kModeHW && mode != kModeOV && mode != kModeSW) return OPAL_B200_ERR_MODE;
@@ -1304,19 +1366,45 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
     (args16 ? list16 : list32).reserve((size_t)n_);
     bool touched = false;
     int emptyFrom = n_;  // keepOnDevice_: first sorted position of the zero-length targets
-    for (int p = 0; p < n_; p++) {
-        const int i = order_[p];
+    int routeFrom = 0;
+    if (!skip && Q > 0) {
+        // Nothing skipped: the classes are ranges of the sorted order (every routing rule is monotone in the target
+        // length): [0, b) needs 32 bits, [b, nonEmpty) fits 16; only the empty targets are left to the loop below.
+        const int m = lay_->nonEmpty;
+        auto ok16 = [&](int T) -> bool {
+            if (isSW) return args16;
+            return track16 ? fits16(T) : (args16 && fits(T, 16000));
+        };
+        int lo = 0, hi = m;  // first position whose target fits 16 bits
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (ok16(lay_->sortedLen[mid])) hi = mid; else lo = mid + 1;
+        }
+        int b = lo;
+        if (!isSW && (b & 1) && b < m) b++;  // a pair is never split between the classes (see below)
+        if (b > 0) {  // the longest target decides whether 32 bits are enough at all
+            const int T = lay_->sortedLen[0];
+            const bool ok32 = isSW ? (maxP > 0 ? (long long)std::min(Q, T) * maxP : 0) < (1LL << 30) : fits(T, 1LL << 30);
+            if (!ok32) return OPAL_B200_ERR_OVERFLOW;
+        }
+        list32.resize((size_t)b);
+        for (int p = 0; p < b; p++) list32[p] = p;
+        list16.resize((size_t)(m - b));
+        for (int p = b; p < m; p++) list16[p - b] = p;
+        touched = m > 0;
+        routeFrom = m;
+    }
+    for (int p = routeFrom; p < n_; p++) {
+        const int i = lay_->order[p];
         if (skip && skip[i]) continue;
-        const int T = sortedLen_[p];
+        const int T = lay_->sortedLen[p];
         if (T == 0 && keepOnDevice_) { emptyFrom = std::min(emptyFrom, p); continue; }  // filled on the device (search_topk)
         if (T == 0 || Q <= 0) {  // nothing to align: defined as in oracle/opal_oracle.c
             int sc = 0, eq = Q - 1, et = T - 1;
             if (Q > 0 && (mode == kModeNW || mode == kModeHW)) sc = -Go - (Q - 1) * Ge;  // the query against one gap
             else if (Q <= 0 && T > 0 && mode == kModeNW) sc = -Go - (T - 1) * Ge;         // ... and the target against one
             if (isSW) { eq = -1; et = -1; }
-            scores[i] = sc;
-            if (endQ) endQ[i] = wantEnd ? eq : -1;
-            if (endT) endT[i] = wantEnd ? et : -1;
+            emit(i, sc, wantEnd ? eq : -1, wantEnd ? et : -1);
             continue;
         }
         touched = true;
@@ -1385,12 +1473,10 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
             parallel_for((long long)list.size(), 65536, [&](long long lo, long long hi) {
                 std::vector<int> flagged;
                 for (long long k = lo; k < hi; k++) {
-                    const int p = list[(size_t)k], i = order_[p];
+                    const int p = list[(size_t)k], i = lay_->order[p];
                     const int sc = hScore_[p];
                     if (sc == kScoreOverflow || sc == kScoreNone) { flagged.push_back(p); continue; }
-                    scores[i] = sc;
-                    if (endQ) endQ[i] = (wantEnd && hEndQ_[p] != 0x7fffffff) ? hEndQ_[p] : -1;
-                    if (endT) endT[i] = (wantEnd && hEndT_[p] != 0x7fffffff) ? hEndT_[p] : -1;
+                    emit(i, sc, (wantEnd && hEndQ_[p] != 0x7fffffff) ? hEndQ_[p] : -1, (wantEnd && hEndT_[p] != 0x7fffffff) ? hEndT_[p] : -1);
                 }
                 if (!flagged.empty()) {
                     std::lock_guard<std::mutex> lk(mu);
@@ -1498,7 +1584,7 @@ int DeviceDb::search_topk(const unsigned char* query, int Q, int Go, int Ge, con
     auto release = [&]() { device_release(device_, dSelect_); dSelect_ = nullptr; keepOnDevice_ = false; };
     if (!dOrder_) {
         if (!ensure_uploaded() || !device_alloc(device_, (void**)&dOrder_, sizeof(int) * (size_t)std::max(n_, 1)) ||
-            cudaMemcpyAsync(dOrder_, order_.data(), sizeof(int) * (size_t)n_, cudaMemcpyHostToDevice, stream_) != cudaSuccess ||
+            cudaMemcpyAsync(dOrder_, lay_->order.data(), sizeof(int) * (size_t)n_, cudaMemcpyHostToDevice, stream_) != cudaSuccess ||
             cudaStreamSynchronize(stream_) != cudaSuccess) {
             set_error("upload of the index map failed"); release(); return OPAL_B200_ERR_CUDA;
         }

@@ -3,7 +3,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/opal.h"
+
 #include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -38,12 +42,43 @@ constexpr int kMaxDevices = 64;  // devices the per-device resource cache is siz
 bool device_alloc(int device, void** p, size_t bytes);
 void device_release(int device, void* p);
 void trim_cache();
+void trim_layouts();
 
 // body(lo, hi) over [0, n) in parts of at least `grain`, on the persistent host pool (the caller takes part).
 void parallel_for(long long n, long long grain, const std::function<void(long long, long long)>& body);
 
 void set_error(const std::string& msg);
 const char* last_error();
+
+// Task lengths of one class (longest first) with strided prefix sums, so that the planner can price any
+// contiguous range of tasks under any group size in O(1).
+struct TaskLens {
+    std::vector<int> len;
+    std::vector<double> prefix[6];  // prefix[s][k] = sum of len[i] over i = 0, g, 2g, ... < k*g with g = 1 << s
+    void build();
+    // sum of len[i] for i = lo, lo+g, ... < hi  (lo must be a multiple of g = 1 << sh), and how many terms
+    double strided(int sh, size_t lo, size_t hi, double* terms) const {
+        const size_t g = (size_t)1 << sh, a = lo / g, b = (hi + g - 1) / g;
+        *terms = (double)(b - a);
+        return prefix[sh][b] - prefix[sh][a];
+    }
+};
+
+// What depends on the sequence lengths alone (engine.cu, "layouts"): shared by every database built from the same
+// length array, immutable once built.
+struct Layout {
+    std::vector<int> lens;                   // the caller's length array (the cache key)
+    std::vector<int> order, pos, sortedLen;  // sorted position -> caller index, its inverse, lengths longest first
+    std::vector<long long> offsets, copyOff; // residue offset of sorted position p / of copy position i (n + 1 entries)
+    std::vector<long long> pairOff, foldOff; // first entry of every pair / folded target in its stream
+    long long total = 0, entries = 0, foldEntries = 0;
+    int numPairs = 0, numFold = 0, nonEmpty = 0;  // nonEmpty: sorted positions [0, nonEmpty) have at least one residue
+    const TaskLens& pair_lens() const;       // planner prefix sums over all non-empty pairs / targets, built on first use
+    const TaskLens& target_lens() const;
+private:
+    mutable std::once_flag pairOnce_, targetOnce_;
+    mutable TaskLens pairLens_, targetLens_;
+};
 
 // A length-sorted (longest first) database resident in one device's HBM.
 class DeviceDb {
@@ -64,8 +99,12 @@ public:
     bool ensure_uploaded();
 
     // Score / score+end for every non-skipped target; outputs in caller order (-1 = unset).
+    // With `records` the results go straight into the caller's OpalSearchResult records instead of the three arrays
+    // (one pass over half a million 40-byte records instead of two); noAlignmentFill also gives every computed record
+    // the fields opalSearchDatabase sets below OPAL_SEARCH_ALIGNMENT (reference src/opal.cpp:1508-1515).
     int search(const unsigned char* query, int Q, int Go, int Ge, const int* matrix, int A, int wantEnd, int mode,
-               const unsigned char* skip, int* scores, int* endQ, int* endT, float* deviceMs);
+               const unsigned char* skip, int* scores, int* endQ, int* endT, float* deviceMs,
+               OpalSearchResult* const* records = nullptr, bool noAlignmentFill = false);
 
     // Score [+ end] search followed by the selection of the k best targets: score descending, then smallest
     // map[caller index] (map NULL: the caller index itself).  Writes k (<= size()) caller indices and their records.
@@ -78,12 +117,12 @@ public:
     int device() const { return device_; }
     cudaStream_t stream() const { return stream_; }
     // sorted position -> caller index, and device-side views (used by the alignment stage)
-    const std::vector<int>& order() const { return order_; }
-    const std::vector<int>& sorted_position() const { return pos_; }
+    const std::vector<int>& order() const { return lay_->order; }
+    const std::vector<int>& sorted_position() const { return lay_->pos; }
     const uint8_t* d_residues() const { return dResidues_; }
     const long long* d_offsets() const { return dOffsets_; }
-    const std::vector<long long>& offsets() const { return offsets_; }
-    const std::vector<int>& sorted_lengths() const { return sortedLen_; }
+    const std::vector<long long>& offsets() const { return lay_->offsets; }
+    const std::vector<int>& sorted_lengths() const { return lay_->sortedLen; }
     const uint8_t* h_residues() const { return hResidues_; }  // pinned host copy, sorted order
 
 private:
@@ -101,8 +140,7 @@ private:
 
     int device_ = 0, n_ = 0, numSMs_ = 0, smemLimit_ = 0;
     long long totalResidues_ = 0;
-    std::vector<int> order_, pos_, sortedLen_;
-    std::vector<long long> offsets_, copyOff_;
+    std::shared_ptr<const Layout> lay_;
     bool ownsDb_ = true, uploaded_ = false;  // search contexts made by clone_context() borrow the database arrays
     std::vector<DeviceDb*> contexts_;
     uint8_t* hResidues_ = nullptr;

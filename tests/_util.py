@@ -87,3 +87,29 @@ def run_forked(fn, timeout=600):
     if status != 0 or not data:
         return None
     return pickle.loads(data)
+
+
+def search_sample_parallel(lib, query, db, sample, go, ge, matrix, alen, search_type, mode, threads=None, results=None):
+    """`lib`.opalSearchDatabase over the sub-database db[sample], split into residue-balanced parts that run on host
+    threads of their own (the checkers are single-threaded per call and re-entrant; ctypes releases the GIL).
+    Returns (rc, records in `sample` order)."""
+    import threading
+    sample = np.asarray(sample, dtype=np.int64)
+    threads = max(1, min(threads or (os.cpu_count() or 1), len(sample)))
+    by_len = np.argsort(-db.lengths[sample].astype(np.int64), kind="stable")
+    parts = [by_len[k::threads] for k in range(threads)]  # dealt longest first: equal work, equal length mix
+    out = new_results(len(sample)) if results is None else results
+    rcs = [0] * threads
+
+    def work(k):
+        sub = db.subset(sample[parts[k]])
+        pre = None if results is None else np.ascontiguousarray(results[parts[k]])
+        rcs[k], res = lib.search_database(query, sub, go, ge, matrix, alen, pre, search_type, mode)
+        out[parts[k]] = res
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return max(rcs), out
