@@ -5,6 +5,9 @@
 // or the "no alignment" field fill -- with the SIMD passes replaced by DeviceDb::search.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -58,28 +61,6 @@ static std::vector<int> env_devices() {
     }
     if (devs.empty()) devs.push_back(default_device());
     return devs;
-}
-
-// Shards balanced by residue count: the sequences in length order (longest first, ties in caller order) are dealt
-// round-robin, so every shard also gets the same length mix -- its longest target is about as long as the others'.
-// index[s] lists the caller indices of shard s in ascending order (sequential reads of the caller's memory).
-static void deal_shards(const int* lens, int n, int parts, std::vector<std::vector<int>>* index) {
-    std::vector<int> order((size_t)n);
-    int maxLen = 0;
-    for (int i = 0; i < n; i++) maxLen = std::max(maxLen, lens[i]);
-    if (maxLen <= (1 << 22)) {  // counting sort
-        std::vector<int> start((size_t)maxLen + 2, 0);
-        for (int i = 0; i < n; i++) start[maxLen - std::max(lens[i], 0) + 1]++;
-        for (int k = 1; k <= maxLen + 1; k++) start[k] += start[k - 1];
-        for (int i = 0; i < n; i++) order[start[maxLen - std::max(lens[i], 0)]++] = i;
-    } else {
-        for (int i = 0; i < n; i++) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lens[a] > lens[b]; });
-    }
-    index->assign((size_t)parts, std::vector<int>());
-    for (auto& v : *index) v.reserve((size_t)n / parts + 1);
-    for (int p = 0; p < n; p++) (*index)[p % parts].push_back(order[p]);
-    for (auto& v : *index) std::sort(v.begin(), v.end());
 }
 
 // fn(s) for every shard, each on a host thread of its own (the caller runs shard 0); returns the first non-zero
@@ -137,7 +118,9 @@ static DbHandle* create_handle(unsigned char* const* db, int n, const int* lens,
         h->residues = h->shards[0]->residues();
         return h;
     }
-    deal_shards(lens, n, parts, &h->index);
+    std::shared_ptr<const Layout> lay = layout_for(lens, nullptr, n, false, nullptr);
+    if (!lay) { delete h; return nullptr; }
+    h->index = *lay->parts(parts, 1);  // dealt in length order: equal residue counts, equal length mix (engine.cu, Layout::parts)
     if (callerIndex)  // keep every shard in ascending CALLER index (ties between equal scores are broken by it, on the device too)
         for (auto& v : h->index) std::sort(v.begin(), v.end(), [&](int a, int b) { return callerIndex[a] < callerIndex[b]; });
     const int rc = on_shards(parts, [&](int s) -> int {
@@ -173,11 +156,21 @@ void opalSearchResultSetScore(OpalSearchResult* r, int score) {  // :1561-1564
     r->score = score;
 }
 
+// Orders the database uploads of the slices of one device (see opalSearchDatabase).
+struct CreateGate {
+    std::mutex mu;
+    std::condition_variable cv;
+    int next = 0;
+    void enter(int ticket) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return next == ticket; }); }
+    void leave() { { std::lock_guard<std::mutex> lk(mu); next++; } cv.notify_all(); }
+};
+
 // The body of opalSearchDatabase once the database is (or can be made) resident.  `ddb` may be NULL: it is
 // then created from db / dbSeqLengths if any entry needs work.  db / dbSeqLengths may be NULL for handle calls.
 static int search_into_results(DeviceDb* ddb, const unsigned char* query, int queryLength, unsigned char* const* db, int dbLength,
                                const int* dbSeqLengths, int gapOpen, int gapExt, const int* scoreMatrix, int alphabetLength,
-                               OpalSearchResult* results[], const int searchType, int mode, int device) {
+                               OpalSearchResult* results[], const int searchType, int mode, int device,
+                               CreateGate* gate = nullptr, int ticket = 0) {
     if (mode != OPAL_MODE_NW && mode != OPAL_MODE_HW && mode != OPAL_MODE_OV && mode != OPAL_MODE_SW)
         return OPAL_ERR_INVALID_MODE;  // :1469-1473, results untouched
     if (dbLength <= 0) return 0;
@@ -205,10 +198,10 @@ static int search_into_results(DeviceDb* ddb, const unsigned char* query, int qu
     };
     const auto t0 = now();
     DeviceDb* owned = nullptr;
-    if (!ddb && (anyWork || searchType == OPAL_SEARCH_ALIGNMENT)) {
-        ddb = owned = DeviceDb::create(db, dbLength, dbSeqLengths, device);
-        if (!ddb) return OPAL_ERR_NO_SIMD_SUPPORT;
-    }
+    if (gate) gate->enter(ticket);  // slices of one device stage and upload in order: the first one's data must land first
+    if (!ddb && (anyWork || searchType == OPAL_SEARCH_ALIGNMENT)) ddb = owned = DeviceDb::create(db, dbLength, dbSeqLengths, device);
+    if (gate) gate->leave();
+    if (!ddb && (anyWork || searchType == OPAL_SEARCH_ALIGNMENT)) return OPAL_ERR_NO_SIMD_SUPPORT;
     const auto t1 = now();
     int status = 0;
     if (anyWork)  // results go straight into the records (same pass also sets the no-alignment fields, :1508-1515)
@@ -244,22 +237,43 @@ int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db
     DeviceGuard guard;
     (void)overflowMethod;  // OPAL_OVERFLOW_SIMPLE / _BUCKETS only schedule the reference's passes; results are equal
     const std::vector<int> devices = env_devices();
-    const int parts = (int)std::min<size_t>(devices.size(), (size_t)std::max(dbLength / 2, 1));
-    if (parts <= 1 || (mode != OPAL_MODE_NW && mode != OPAL_MODE_HW && mode != OPAL_MODE_OV && mode != OPAL_MODE_SW))
+    const int D = (int)std::min<size_t>(devices.size(), (size_t)std::max(dbLength / 2, 1));
+    const bool modeOk = mode == OPAL_MODE_NW || mode == OPAL_MODE_HW || mode == OPAL_MODE_OV || mode == OPAL_MODE_SW;
+    // A large database is cut into a few SLICES per device (longest sequences first) that are staged, uploaded and
+    // searched as databases of their own, each on a host thread and streams of its own: the first slice is being
+    // searched while the others are still on their way, and a slice's records are written while the next one's kernels
+    // run -- per call, the staging, the copies and the result writes then overlap the kernels instead of preceding
+    // and following them.
+    long long total = 0;
+    for (int i = 0; i < dbLength && modeOk; i++) total += dbSeqLengths[i] > 0 ? dbSeqLengths[i] : 0;
+    int K = (int)std::max<long long>(1, std::min<long long>(4, total / std::max(D, 1) / (48LL << 20)));
+    if (const char* e = getenv("OPAL_B200_SLICES")) K = std::max(1, std::min(atoi(e), 16));
+    K = std::min(K, std::max(dbLength / (2 * std::max(D, 1)), 1));
+    if (D * K <= 1 || !modeOk)
         return search_into_results(nullptr, query, queryLength, db, dbLength, dbSeqLengths, gapOpen, gapExt, scoreMatrix,
                                    alphabetLength, results, searchType, mode, devices[0]);
-    // One call = the whole database (reference src/opal.h:150-154), on every listed device: each searches the shard
-    // dealt to it and fills the caller's records of that shard; the alignment stage stays on the owning device.
-    std::vector<std::vector<int>> index;
-    deal_shards(dbSeqLengths, dbLength, parts, &index);
-    return on_shards(parts, [&](int s) -> int {
-        const std::vector<int>& idx = index[s];
+    // One call = the whole database (reference src/opal.h:150-154), on every listed device: each searches the parts
+    // dealt to it and fills the caller's records of those parts; the alignment stage stays on the owning device.
+    std::shared_ptr<const Layout> lay = layout_for(dbSeqLengths, nullptr, dbLength, false, nullptr);
+    if (!lay) return OPAL_ERR_NO_SIMD_SUPPORT;
+    const std::shared_ptr<const std::vector<std::vector<int>>> parts = lay->parts(D, K);
+    std::vector<CreateGate> gates((size_t)D);
+    return on_shards(D * K, [&](int s) -> int {
+        const int d = s / K, k = s % K;
+        const std::vector<int>& idx = (*parts)[(size_t)s];
+        if (idx.empty()) {  // nothing dealt to this slice: let the next one through
+            if (K > 1) { gates[d].enter(k); gates[d].leave(); }
+            return 0;
+        }
         std::vector<unsigned char*> ptr(idx.size());
         std::vector<int> len(idx.size());
         std::vector<OpalSearchResult*> res(idx.size());
-        for (size_t k = 0; k < idx.size(); k++) { ptr[k] = db[idx[k]]; len[k] = dbSeqLengths[idx[k]]; res[k] = results[idx[k]]; }
-        return search_into_results(nullptr, query, queryLength, ptr.data(), (int)idx.size(), len.data(), gapOpen, gapExt, scoreMatrix,
-                                   alphabetLength, res.data(), searchType, mode, devices[s]);
+        for (size_t j = 0; j < idx.size(); j++) { ptr[j] = db[idx[j]]; len[j] = dbSeqLengths[idx[j]]; res[j] = results[idx[j]]; }
+        set_thread_overlapped(k + 1 < K);  // other slices follow on this device: plan for throughput, not for the last task's end
+        const int rc = search_into_results(nullptr, query, queryLength, ptr.data(), (int)idx.size(), len.data(), gapOpen, gapExt,
+                                           scoreMatrix, alphabetLength, res.data(), searchType, mode, devices[d], K > 1 ? &gates[d] : nullptr, k);
+        set_thread_overlapped(false);
+        return rc;
     });
 }
 

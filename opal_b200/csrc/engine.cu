@@ -370,6 +370,32 @@ const TaskLens& Layout::target_lens() const {
     return targetLens_;
 }
 
+// Parts of a database for several devices and / or pipelined slices.  Devices: the sorted order is dealt round-robin
+// (equal residue count, equal length mix -- every device's longest target is about as long as the others').  Slices
+// of one device: contiguous runs of ITS sorted order with equal residue counts, longest sequences first, so that the
+// first slice to be uploaded holds the long targets whose single-warp sweeps last longest and every later slice is
+// searched while the next one is still on its way.
+std::shared_ptr<const std::vector<std::vector<int>>> Layout::parts(int devices, int perDevice) const {
+    std::lock_guard<std::mutex> lk(partsMu_);
+    for (const auto& e : parts_)
+        if (e.first.first == devices && e.first.second == perDevice) return e.second;
+    auto out = std::make_shared<std::vector<std::vector<int>>>((size_t)devices * perDevice);
+    const int n = (int)order.size();
+    for (int d = 0; d < devices; d++) {
+        long long mine = 0;
+        for (int p = d; p < n; p += devices) mine += sortedLen[p];
+        long long seen = 0;
+        for (int p = d; p < n; p += devices) {
+            const int k = (int)std::min<long long>(perDevice - 1, mine > 0 ? seen * perDevice / mine : 0);
+            (*out)[(size_t)d * perDevice + k].push_back(order[p]);
+            seen += sortedLen[p];
+        }
+    }
+    for (auto& v : *out) std::sort(v.begin(), v.end());  // ascending caller index: sequential reads of the caller's memory
+    parts_.push_back({{devices, perDevice}, out});
+    return out;
+}
+
 namespace {
 std::mutex g_layoutMu;
 std::vector<std::shared_ptr<Layout>> g_layouts;  // most recently used last
@@ -455,6 +481,7 @@ static thread_local int t_forceK = 0, t_forceG = 0, t_forceR = 0;  // developmen
 // mostly by the SM time it takes, not by when its last task ends.  Measured on BASELINE configs[1], 32 queries with
 // three in flight: plans with three warps per partition give 3975 - 4010 GCUPS, the single-search optimum 3770.
 static thread_local bool t_overlapped = false;
+void set_thread_overlapped(bool on) { t_overlapped = on; }
 
 static bool pick_geometry(int Q, int A, int lanes, const TaskLens& tl, size_t lo, size_t hi, int smemLimit, int numSMs, int mode,
                           bool latencyClass, int flavorClass, Geometry* out, double* estCycles, bool folded = false) {

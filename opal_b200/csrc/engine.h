@@ -75,10 +75,20 @@ struct Layout {
     int numPairs = 0, numFold = 0, nonEmpty = 0;  // nonEmpty: sorted positions [0, nonEmpty) have at least one residue
     const TaskLens& pair_lens() const;       // planner prefix sums over all non-empty pairs / targets, built on first use
     const TaskLens& target_lens() const;
+    // The database cut into devices x perDevice parts (engine.cu: Layout::parts): caller indices of every part,
+    // ascending; part d * perDevice + k is slice k of device d.  Built on first use, remembered with the layout.
+    std::shared_ptr<const std::vector<std::vector<int>>> parts(int devices, int perDevice) const;
 private:
     mutable std::once_flag pairOnce_, targetOnce_;
     mutable TaskLens pairLens_, targetLens_;
+    mutable std::mutex partsMu_;
+    mutable std::vector<std::pair<std::pair<int, int>, std::shared_ptr<const std::vector<std::vector<int>>>>> parts_;
 };
+// The layout of a database: from the cache, or built (and remembered when the database is scattered).
+std::shared_ptr<const Layout> layout_for(const int* lens, const int* order, int n, bool packed, bool* cached);
+// The calling thread's searches are followed by others on the same device (batches, slices): plans are priced by the
+// SM time they hold rather than by when their last task ends.
+void set_thread_overlapped(bool on);
 
 // A length-sorted (longest first) database resident in one device's HBM.
 class DeviceDb {

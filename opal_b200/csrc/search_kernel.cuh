@@ -282,28 +282,42 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
     const int G = p.G, Go = p.gapOpen, Ge = p.gapExt, A = p.A, mode = p.mode;
     const int planeWords = (A + 1) * p.rowStride;
 
-    // ---- build the query profile for this pass
-    for (int idx = threadIdx.x; idx < planeWords; idx += blockDim.x) {
-        const int row = idx / p.rowStride, pos = idx - row * p.rowStride;
+    // ---- build the query profile for this pass.  One thread per profile COLUMN (a padded query row of some thread's
+    // strip): it reads its query letter once -- the only load with global-memory latency -- and then walks down the
+    // A + 1 target letters of that column, reading one row of the score matrix (a few cache lines).  (The earlier form,
+    // one thread per profile WORD, paid the query load and its dependent matrix load for every word: ~40 us per launch
+    // at 32 x 33 rows, which is 6 % of a BASELINE configs[1] search and 1 - 2 % of every pass on a database shard.)
+    for (int pos = threadIdx.x; pos < p.rowStride; pos += blockDim.x) {
         const int t = pos / p.Rpad, j = pos - t * p.Rpad;
-        int sc = Go, scHi = Go;  // padding rows score 0 against everything (keeps H = 0 above the query)
-        if (t < G && j < R) {
+        int q = -1, q2 = -1;  // query letters of the low / high half-word rows; -1 = padding row
+        const bool used = t < G && j < R;
+        if (used) {
             const int r = p.rowBase + t * R + j - p.padTop;
-            if (r >= 0 && r < p.Q) sc = ((row > 0) ? p.matrix[(int)p.query[r] * A + row - 1] : p.padLetterScore) + Go;
-            else if (row == 0) sc = p.padLetterScore + Go;
-            scHi = sc;
+            if (r >= 0 && r < p.Q) q = p.query[r];
+            q2 = q;
             if (LANES == 2 && p.folded) {  // high half-words: the rows 32 R further down
                 const int r2 = r + 32 * R;
-                scHi = Go;
-                if (r2 >= 0 && r2 < p.Q) scHi = ((row > 0) ? p.matrix[(int)p.query[r2] * A + row - 1] : p.padLetterScore) + Go;
-                else if (row == 0) scHi = p.padLetterScore + Go;
+                q2 = (r2 >= 0 && r2 < p.Q) ? (int)p.query[r2] : -1;
             }
         }
-        if (LANES == 2) {
-            smem[idx] = (uint32_t)sc & 0xffffu;
-            smem[planeWords + idx] = (uint32_t)scHi << 16;
-        } else {
-            smem[idx] = (uint32_t)sc;
+        // padding rows score 0 against everything (keeps H = 0 above the query); letter 0 is "no residue"
+        const int* mrow = p.matrix + (q >= 0 ? q : 0) * A;
+        const int* mrow2 = p.matrix + (q2 >= 0 ? q2 : 0) * A;
+        for (int row = 0; row <= A; row++) {
+            int sc = Go, scHi = Go;
+            if (used) {
+                if (row == 0) sc = scHi = p.padLetterScore + Go;
+                if (q >= 0 && row > 0) sc = mrow[row - 1] + Go;
+                if (q2 >= 0 && row > 0) scHi = mrow2[row - 1] + Go;
+                if (!(LANES == 2 && p.folded)) scHi = sc;
+            }
+            const int idx = row * p.rowStride + pos;
+            if (LANES == 2) {
+                smem[idx] = (uint32_t)sc & 0xffffu;
+                smem[planeWords + idx] = (uint32_t)scHi << 16;
+            } else {
+                smem[idx] = (uint32_t)sc;
+            }
         }
     }
     __syncthreads();

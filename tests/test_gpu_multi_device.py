@@ -145,3 +145,38 @@ def test_packed_database_on_several_devices(product):
     finally:
         h1.close()
         hn.close()
+
+
+@pytest.mark.parametrize("mode", ["SW", "HW"])
+def test_drop_in_call_in_pipelined_slices(product, oracle, mode, monkeypatch):
+    """A large database goes through the drop-in call in slices (longest sequences first) whose uploads and searches
+    overlap; OPAL_B200_SLICES forces that on a small one.  Records must not depend on the number of slices, alone or
+    combined with several devices."""
+    rng = np.random.default_rng(35)
+    sm = matrices.blosum62()
+    q = datasets.random_residues(140, rng, sm)
+    db = _db(rng, sm, 350, q)
+    monkeypatch.delenv("OPAL_B200_DEVICES", raising=False)
+    monkeypatch.delenv("OPAL_B200_SLICES", raising=False)
+    for st in (0, 1, 2):
+        rc1, one = product.search_database(q, db, 11, 1, sm.flat(), 23, None, st, MODES[mode])
+        assert rc1 == 0
+        want = dump_results(one)
+        free_alignments(one)
+        for slices, devs in ((3, None), (2, "0,0"), (16, None)):
+            monkeypatch.setenv("OPAL_B200_SLICES", str(slices))
+            if devs:
+                monkeypatch.setenv("OPAL_B200_DEVICES", devs)
+            rc, res = product.search_database(q, db, 11, 1, sm.flat(), 23, None, st, MODES[mode])
+            assert rc == 0, product.last_error()
+            assert dump_results(res) == want, (st, slices, devs)
+            free_alignments(res)
+            monkeypatch.delenv("OPAL_B200_SLICES")
+            monkeypatch.delenv("OPAL_B200_DEVICES", raising=False)
+    rc, want = search_dump(oracle, q, db, 11, 1, sm.flat(), 23, 1, MODES[mode])
+    monkeypatch.setenv("OPAL_B200_SLICES", "4")
+    rc2, got = search_dump(product, q, db, 11, 1, sm.flat(), 23, 1, MODES[mode])
+    assert rc == 0 and rc2 == 0 and got == want
+    # invalid arguments still come back as such from every slice
+    rc, _ = product.search_database(np.array([0, 99], dtype=np.uint8), db, 11, 1, sm.flat(), 23, None, 0, MODES[mode])
+    assert rc == 4
