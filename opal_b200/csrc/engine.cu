@@ -255,18 +255,22 @@ public:
     static HostPool& get() { static HostPool* p = new HostPool(); return *p; }  // leaked on purpose, like the cache
     int width() const { return (int)workers_.size() + 1; }
     // Runs fn(part) for part in [0, parts); done(part) is called on the calling thread, in part order, as soon as
-    // parts 0..part have all finished.  One job at a time: a second concurrent caller simply runs its job alone.
+    // parts 0..part have all finished.  Several callers may have jobs in the pool at once (the slices and devices of
+    // one drop-in call stage, publish and write records concurrently): workers take parts from whichever job has some
+    // left, and every caller works on its own job until it is through.
     void run(int parts, const std::function<void(int)>& fn, const std::function<void(int)>& done) {
-        std::unique_lock<std::mutex> job(jobMu_, std::try_to_lock);
-        if (!job.owns_lock() || workers_.empty() || parts <= 1) {
+        if (workers_.empty() || parts <= 1) {
             for (int k = 0; k < parts; k++) { fn(k); done(k); }
             return;
         }
+        Job job;
+        job.fn = &fn; job.parts = parts;
         std::vector<std::atomic<char>> finished((size_t)parts);
         for (auto& f : finished) f.store(0, std::memory_order_relaxed);
+        job.finished = finished.data();
         {
             std::lock_guard<std::mutex> lk(mu_);
-            fn_ = &fn; finished_ = finished.data(); parts_ = parts; next_.store(0); active_ = 0; generation_++;
+            jobs_.push_back(&job);
         }
         cv_.notify_all();
         int reported = 0;
@@ -274,20 +278,26 @@ public:
             while (reported < parts && finished[reported].load(std::memory_order_acquire)) done(reported++);
         };
         for (;;) {
-            const int k = next_.fetch_add(1);
+            const int k = job.next.fetch_add(1);
             if (k >= parts) break;
             fn(k);
             finished[k].store(1, std::memory_order_release);
             report();
         }
         while (reported < parts) { report(); std::this_thread::yield(); }
-        // workers may still be between "claimed nothing" and going back to sleep: wait until none holds fn_
+        // the job leaves the list; workers that still hold it (between taking a part number and finding none left) let go first
         std::unique_lock<std::mutex> lk(mu_);
-        fn_ = nullptr;
-        idle_.wait(lk, [&] { return active_ == 0; });
+        jobs_.erase(std::find(jobs_.begin(), jobs_.end(), &job));
+        idle_.wait(lk, [&] { return job.holders == 0; });
     }
 
 private:
+    struct Job {
+        const std::function<void(int)>* fn = nullptr;
+        std::atomic<char>* finished = nullptr;
+        int parts = 0, holders = 0;  // holders: workers inside this job (guarded by mu_)
+        std::atomic<int> next{0};
+    };
     HostPool() {
         int width = std::min((int)std::thread::hardware_concurrency(), 16);
         if (const char* e = getenv("OPAL_B200_HOST_THREADS")) width = std::max(1, std::min(atoi(e), 64));
@@ -296,39 +306,37 @@ private:
         for (auto& t : workers_) t.detach();
     }
     void loop() {
-        unsigned seen = 0;
+        size_t turn = 0;
         for (;;) {
-            const std::function<void(int)>* fn;
-            std::atomic<char>* finished;
-            int parts;
+            Job* job = nullptr;
             {
                 std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return generation_ != seen && fn_ != nullptr; });
-                seen = generation_;
-                fn = fn_; finished = finished_; parts = parts_;
-                active_++;
+                cv_.wait(lk, [&] {
+                    for (size_t i = 0; i < jobs_.size(); i++) {  // round-robin over the jobs that still have parts to hand out
+                        Job* j = jobs_[(turn + i) % jobs_.size()];
+                        if (j->next.load(std::memory_order_relaxed) < j->parts) { job = j; turn += i + 1; return true; }
+                    }
+                    return false;
+                });
+                job->holders++;
             }
             for (;;) {
-                const int k = next_.fetch_add(1);
-                if (k >= parts) break;
-                (*fn)(k);
-                finished[k].store(1, std::memory_order_release);
+                const int k = job->next.fetch_add(1);
+                if (k >= job->parts) break;
+                (*job->fn)(k);
+                job->finished[k].store(1, std::memory_order_release);
             }
             {
                 std::lock_guard<std::mutex> lk(mu_);
-                active_--;
+                job->holders--;
             }
             idle_.notify_all();
         }
     }
     std::vector<std::thread> workers_;
-    std::mutex jobMu_, mu_;
+    std::mutex mu_;
     std::condition_variable cv_, idle_;
-    const std::function<void(int)>* fn_ = nullptr;
-    std::atomic<char>* finished_ = nullptr;
-    int parts_ = 0, active_ = 0;
-    unsigned generation_ = 0;
-    std::atomic<int> next_{0};
+    std::vector<Job*> jobs_;
 };
 }  // namespace
 
@@ -925,10 +933,10 @@ DeviceDb* DeviceDb::build(unsigned char* const* db, const unsigned char* packed,
         // far larger than the caches.
         HostPool& pool = HostPool::get();
         const bool oneRun = packed || (n > 0 && db[n - 1] + lens[n - 1] == db[0] + total);  // the usual arena-loaded database
-        int stageThreads = total >= (64LL << 20) ? pool.width() : (oneRun && total >= (2 << 20) ? std::min(pool.width(), 8) : 1);
+        int stageThreads = total >= (16LL << 20) ? pool.width() : (oneRun && total >= (2 << 20) ? std::min(pool.width(), 8) : 1);
         if (const char* e = getenv("OPAL_B200_STAGE_THREADS")) stageThreads = std::max(1, std::min(atoi(e), pool.width()));
         const bool threaded = stageThreads > 1;
-        const long long partBytes = total >= (64LL << 20) ? (8 << 20) : std::max<long long>(256 << 10, total / stageThreads);
+        const long long partBytes = total >= (64LL << 20) ? (8 << 20) : std::max<long long>(256 << 10, total / (2 * stageThreads));
         const int parts = (int)std::max<long long>(1, std::min<long long>(total / partBytes, 4096));
         std::vector<int> cut((size_t)parts + 1, n);
         cut[0] = 0;
