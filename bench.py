@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from opal_b200 import (MODES, OPAL_OVERFLOW_BUCKETS, OPAL_SEARCH_SCORE, OPAL_SEARCH_SCORE_END, OpalCLibrary,  # noqa: E402
-                       SequenceDB, datasets, matrices, new_results, sharding)
+                       SequenceDB, datasets, matrices, new_results, result_pointers, sharding)
 
 GAP_OPEN, GAP_EXT = 11, 1
 CPU_MAX_TARGET = 20000  # the reference's NW/HW/OV 32-bit pass is undefined behaviour: keep it out of the CPU sample
@@ -149,6 +149,7 @@ def cpu_sweep(lib, w, shards):
     sm = w.sm
     results = [new_results(len(s)) for s in shards]
     blank = [r.copy() for r in results]
+    ptrs = [result_pointers(r) for r in results]
     rcs = [0] * len(shards)
 
     def work(k):
@@ -156,7 +157,7 @@ def cpu_sweep(lib, w, shards):
             for q in w.queries:
                 np.copyto(results[k].view(np.uint8), blank[k].view(np.uint8))
                 rc, _ = lib.search_database(q, shards[k], GAP_OPEN, GAP_EXT, sm.flat(), sm.alphabet_length, results[k],
-                                            w.search_type, MODES[mode], OPAL_OVERFLOW_BUCKETS)
+                                            w.search_type, MODES[mode], OPAL_OVERFLOW_BUCKETS, result_ptrs=ptrs[k])
                 rcs[k] |= rc
 
     threads = [threading.Thread(target=work, args=(k,)) for k in range(len(shards))]
@@ -302,12 +303,14 @@ def run_b200_arm(args, rank, local_rank, world):
     blank = new_results(n)
     res = blank.copy()
     res_bytes, blank_bytes = res.view(np.uint8), blank.view(np.uint8)  # flat views: the reset below is one memcpy
+    res_ptrs = result_pointers(res)  # the OpalSearchResult* array a C caller holds
 
     def step_e2e():
         for mode in w.modes:
             for q in w.queries:
                 np.copyto(res_bytes, blank_bytes)  # the caller's opalInitSearchResult loop (reference src/opal_aligner.cpp:150-154)
-                rc, _ = eng.search_database(q, db, GAP_OPEN, GAP_EXT, mat, A, res, w.search_type, MODES[mode], OPAL_OVERFLOW_BUCKETS)
+                rc, _ = eng.search_database(q, db, GAP_OPEN, GAP_EXT, mat, A, res, w.search_type, MODES[mode], OPAL_OVERFLOW_BUCKETS,
+                                            result_ptrs=res_ptrs)
                 if rc != 0:
                     raise SystemExit(f"opalSearchDatabase failed rc={rc}: {eng.last_error()}")
 
@@ -341,12 +344,14 @@ def run_b200_arm(args, rank, local_rank, world):
             blank_full = new_results(len(full))
             res_full = blank_full.copy()
             rf_bytes, bf_bytes = res_full.view(np.uint8), blank_full.view(np.uint8)
+            rf_ptrs = result_pointers(res_full)
 
             def sweep_all_devices():
                 for mode in w.modes:
                     for q in w.queries:
                         np.copyto(rf_bytes, bf_bytes)
-                        rc, _ = eng.search_database(q, full, GAP_OPEN, GAP_EXT, mat, A, res_full, w.search_type, MODES[mode], OPAL_OVERFLOW_BUCKETS)
+                        rc, _ = eng.search_database(q, full, GAP_OPEN, GAP_EXT, mat, A, res_full, w.search_type, MODES[mode], OPAL_OVERFLOW_BUCKETS,
+                                                    result_ptrs=rf_ptrs)
                         if rc != 0:
                             raise SystemExit(f"opalSearchDatabase on {world} devices failed rc={rc}: {eng.last_error()}")
 

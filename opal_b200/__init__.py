@@ -10,5 +10,5 @@ from .capi import (  # noqa: F401
     OPAL_ERR_NO_SIMD_SUPPORT, OPAL_ERR_OVERFLOW, OPAL_MODE_HW, OPAL_MODE_NW, OPAL_MODE_OV,
     OPAL_MODE_SW, OPAL_OVERFLOW_BUCKETS, OPAL_OVERFLOW_SIMPLE, OPAL_SEARCH_ALIGNMENT,
     OPAL_SEARCH_SCORE, OPAL_SEARCH_SCORE_END, MODES, OpalCLibrary, SequenceDB, free_alignments,
-    get_alignment, new_results)
+    get_alignment, new_results, result_pointers)
 from . import sharding  # noqa: F401,E402

@@ -25,6 +25,7 @@ import numpy as np
 OPAL_ERR_OVERFLOW = 1
 OPAL_ERR_NO_SIMD_SUPPORT = 2
 OPAL_ERR_INVALID_MODE = 3
+OPAL_ERR_INVALID_ARGUMENT = 4  # addition of opal-b200 (include/opal.h)
 OPAL_MODE_NW, OPAL_MODE_HW, OPAL_MODE_OV, OPAL_MODE_SW = 0, 1, 2, 3
 OPAL_OVERFLOW_SIMPLE, OPAL_OVERFLOW_BUCKETS = 0, 1
 OPAL_SEARCH_SCORE, OPAL_SEARCH_SCORE_END, OPAL_SEARCH_ALIGNMENT = 0, 1, 2
@@ -156,14 +157,15 @@ class OpalCLibrary:
 
     def search_database(self, query, db: SequenceDB, gap_open, gap_ext, score_matrix, alphabet_length,
                         results=None, search_type=OPAL_SEARCH_SCORE, mode=OPAL_MODE_SW,
-                        overflow_method=OPAL_OVERFLOW_BUCKETS, entry="opalSearchDatabase"):
-        """opalSearchDatabase (reference src/opal.h:150-154). Returns (rc, results)."""
+                        overflow_method=OPAL_OVERFLOW_BUCKETS, entry="opalSearchDatabase", result_ptrs=None):
+        """opalSearchDatabase (reference src/opal.h:150-154). Returns (rc, results).  `result_ptrs`: the array of
+        record pointers a caller that reuses its records keeps (result_pointers(results)), instead of rebuilding it."""
         query = np.ascontiguousarray(query, dtype=np.uint8)
         sm = np.ascontiguousarray(score_matrix, dtype=np.int32).ravel()
         assert sm.size == alphabet_length * alphabet_length
         if results is None:
             results = new_results(len(db))
-        rp = result_pointers(results)
+        rp = result_pointers(results) if result_ptrs is None else result_ptrs
         qbuf = query if query.size else np.zeros(1, dtype=np.uint8)
         rc = getattr(self.lib, entry)(
             qbuf.ctypes.data, int(query.size), db.pointers.ctypes.data, len(db), db.lengths.ctypes.data,

@@ -246,7 +246,7 @@ int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db
     // and following them.
     long long total = 0;
     for (int i = 0; i < dbLength && modeOk; i++) total += dbSeqLengths[i] > 0 ? dbSeqLengths[i] : 0;
-    int K = (int)std::max<long long>(1, std::min<long long>(4, total / std::max(D, 1) / (48LL << 20)));
+    int K = total / std::max(D, 1) >= (96LL << 20) ? 4 : total / std::max(D, 1) >= (32LL << 20) ? 3 : 1;
     if (const char* e = getenv("OPAL_B200_SLICES")) K = std::max(1, std::min(atoi(e), 16));
     K = std::min(K, std::max(dbLength / (2 * std::max(D, 1)), 1));
     if (D * K <= 1 || !modeOk)
