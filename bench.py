@@ -33,6 +33,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# Searches in flight use streams of their own; with the default 8 hardware queues unrelated streams wait for each
+# other's launches (libopal_b200.so sets this itself when it is loaded first; here torch initialises CUDA before it).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from opal_b200 import (MODES, OPAL_OVERFLOW_BUCKETS, OPAL_SEARCH_SCORE, OPAL_SEARCH_SCORE_END, OpalCLibrary,  # noqa: E402
                        SequenceDB, datasets, matrices, new_results, result_pointers, sharding)
@@ -458,7 +461,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config3", choices=["config2", "config3"])
-    ap.add_argument("--in-flight", type=int, default=4, help="queries of a batch on the device at a time")
+    ap.add_argument("--in-flight", type=int, default=12, help="queries of a batch on the device at a time")
     ap.add_argument("--order", default="desc", choices=["desc", "interleave"], help="order of the queries within a step")
     ap.add_argument("--shard-of", type=int, default=0, help="development: run one shard of an M-way deal on one GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
