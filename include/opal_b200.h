@@ -135,6 +135,12 @@ void opalb200_db_last_stats(const OpalB200Db* handle, int* kernelLaunches, int* 
  * database -- each bounds the search time, being swept by a single warp -- are finished sooner. 0 = none. */
 int opalb200_db_last_folded(const OpalB200Db* handle);
 
+/* Tasks of the last search whose passes over the query were "chained": a query longer than one strip of rows takes
+ * several passes, and for the longest targets every pass runs on a warp of its own at the same time, the boundary row
+ * handed from pass to pass through L2 while both sweep -- the target then costs its length in steps once, not once per
+ * pass. 0 = none. */
+int opalb200_db_last_chained(const OpalB200Db* handle);
+
 /*
  * Measures the packed-DPX issue rate of `device` with a register-only kernel running the SW cell
  * recurrence (6 s16x2 instructions per 2 cells): returns giga cell updates per second that the

@@ -108,6 +108,7 @@ struct DbHandle {
             stats.kernelLaunches += shards[s]->stats().kernelLaunches;
             stats.rerun32 += shards[s]->stats().rerun32;
             stats.foldedTasks += shards[s]->stats().foldedTasks;
+            stats.chainedTasks += shards[s]->stats().chainedTasks;
         }
     }
 };
@@ -572,6 +573,8 @@ void opalb200_db_last_stats(const OpalB200Db* h, int* kernelLaunches, int* rerun
 }
 
 int opalb200_db_last_folded(const OpalB200Db* h) { return reinterpret_cast<const DbHandle*>(h)->stats.foldedTasks; }
+
+int opalb200_db_last_chained(const OpalB200Db* h) { return reinterpret_cast<const DbHandle*>(h)->stats.chainedTasks; }
 
 double opalb200_measure_dpx_peak(int device, double* threadInstrPerSec, float* ms) {
     DeviceGuard guard;

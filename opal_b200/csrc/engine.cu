@@ -1048,6 +1048,7 @@ DeviceDb::~DeviceDb() {
     if (stream_) cudaStreamSynchronize(stream_);
     void* own[] = {dResults_, dArgs_, dBndH_, dBndF_};
     for (void* p : own) device_release(device_, p);
+    for (void* b : chainScratch_) device_release(device_, b);
     if (ownsDb_) {
         void* shared[] = {dBlock_, dPairStream_, dFoldStream_, dOrder_};
         for (void* p : shared) device_release(device_, p);
@@ -1153,6 +1154,38 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
                 }
             }
         }
+        // Chained variant of the latency class for queries that take several passes: every pass of a task on a warp
+        // of its own, all of them sweeping at once (SearchParams::chain) -- passes x quads SMs, but the longest target
+        // costs its length in steps once, not once per pass.  Priced for a few strip heights: shorter strips mean
+        // faster steps and more SMs.
+        if (!getenv("OPAL_B200_NO_CHAIN") && fm < 0) {
+            const auto& tables = kernel_tables();
+            const int planes = lanes == 2 ? 2 : 1;
+            const bool force = getenv("OPAL_B200_CHAIN") != nullptr;  // tests: chain whenever there are several passes
+            for (size_t m = 4; m * 2 <= nT && m <= 32; m *= 2) {
+                const int quads = (int)((m + 3) / 4);
+                for (size_t ti = 0; ti < tables.size(); ti++) {
+                    const int R = tables[ti].R;
+                    if (R != 6 && R != 9 && R != 12 && R != 17 && R != 24 && R != 33) continue;
+                    const int rows = 32 * R, passes = (Q + rows - 1) / rows;
+                    if (passes < 2 || passes > 64) continue;
+                    if ((long long)passes * rows * 3 > (long long)Q * 4 + 96) continue;  // more than a third padding
+                    const int Rpad = rpad_of(R), rowStride = 32 * Rpad;
+                    const size_t smem = (size_t)planes * (A + 1) * rowStride * 4;
+                    const int smL = passes * quads;
+                    if (smem > (size_t)smemLimit_ || smL > numSMs_ / 3) continue;
+                    Geometry gL, gB;
+                    gL.G = 32; gL.R = R; gL.tableIndex = (int)ti; gL.passes = passes; gL.Rpad = Rpad; gL.rowStride = rowStride;
+                    gL.smemBytes = smem; gL.warpsPerPartition = 1; gL.padTop = mode == kModeNW ? 0 : passes * rows - Q; gL.chain = true;
+                    // every pass trails the one above by about three chunks of 32 columns
+                    const double tL = (tl.len[0] + 31 + 96.0 * (passes - 1)) * step_cycles(flavorClass, 1, R) * 1.03 + 30000.0;
+                    double tB = 0;
+                    if (!pick_geometry(Q, A, lanes, tl, m, nT, smemLimit_, numSMs_ - smL, mode, false, flavorClass, &gB, &tB)) continue;
+                    const double t = (t_overlapped ? (smL * tL + (numSMs_ - smL) * tB) / numSMs_ : std::max(tL, tB)) + 3000.0;
+                    if (t < bestT * 0.97 || (force && !bestL.chain)) { bestT = t; bestM = m; bestSm = smL; bestL = gL; bestB = gB; }
+                }
+            }
+        }
         t_forceK = t_forceG = t_forceR = 0;
     }
     auto add = [&](size_t lo, size_t hi, const Geometry& g, int maxBlocks, size_t otherSmem, double est) {
@@ -1202,7 +1235,7 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
                             const int* dMatrix, int Q, int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot) {
     const Geometry& g = grp.g;
     const int type = grp.type;
-    if (g.passes > 1 && !ensure_boundary()) return false;
+    if (g.passes > 1 && !g.chain && !ensure_boundary()) return false;
     if (*launchSlot + g.passes > 256) { set_error("too many passes"); return false; }
     // contiguous task ranges need no list in device memory
     bool contiguous = true;
@@ -1219,7 +1252,29 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
     if (flavor == kFlavorGlobal && 128 * g.warpsPerPartition > launch_bound_for(flavor, g.R))
         fn = kernel_tables()[g.tableIndex].fn[type == 0 ? 8 : type * 4 + flavor];  // Packed16 variant compiled for 384 threads
     if (!allow_full_smem(device_, fn, smemLimit_)) return false;
-    for (int pass = 0; pass < g.passes; pass++) {
+    // chained passes: one launch, passes x quads blocks; boundary rows and flags live in a block of their own
+    int chainStride = 0;
+    int *dChainOffsets = nullptr, *dChainProgress = nullptr, *dChainDone = nullptr, *dChainTicket = nullptr;
+    uint32_t *dChainH = nullptr, *dChainF = nullptr;
+    if (g.chain) {
+        std::vector<int> offsets(grp.tasks.size());
+        for (size_t k = 0; k < grp.tasks.size(); k++) {
+            offsets[k] = chainStride;
+            chainStride += lay_->sortedLen[type == 0 ? 2 * (size_t)grp.tasks[k] : (size_t)grp.tasks[k]] + 32;
+        }
+        chainStride = (chainStride + 63) / 64 * 64;
+        const size_t nT = grp.tasks.size(), flags = nT * (size_t)g.passes;
+        const size_t ints = nT + 2 * flags + 64, words = 2 * (size_t)g.passes * (size_t)chainStride;
+        int* block = nullptr;
+        if (!device_alloc(device_, (void**)&block, sizeof(int) * (ints + words))) return false;
+        chainScratch_.push_back(block);
+        dChainOffsets = block; dChainProgress = block + nT; dChainDone = dChainProgress + flags; dChainTicket = dChainDone + flags;
+        dChainH = reinterpret_cast<uint32_t*>(block + ints); dChainF = dChainH + (size_t)g.passes * chainStride;
+        CUDA_TRY(cudaMemsetAsync(block, 0, sizeof(int) * ints, stream));
+        CUDA_TRY(cudaMemcpyAsync(dChainOffsets, offsets.data(), sizeof(int) * nT, cudaMemcpyHostToDevice, stream));  // (pageable: staged before the call returns)
+        stats_.chainedTasks = (int)nT;
+    }
+    for (int pass = 0; pass < (g.chain ? 1 : g.passes); pass++) {
         SearchParams p;
         memset(&p, 0, sizeof(p));
         p.query = dQuery; p.matrix = dMatrix; p.Q = Q; p.A = A; p.gapOpen = Go; p.gapExt = Ge; p.mode = mode;
@@ -1249,10 +1304,16 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
             p.rangeHi = rangeTracking_ ? (int)(32767 - margin) : INT_MAX;   // (not tracking: routed by the a-priori bound)
             p.rangeLo = rangeTracking_ ? (int)((mode == kModeNW ? -28000 : -16383) + margin) : INT_MIN;
         }
+        if (g.chain) {
+            p.chain = 1; p.chainStride = chainStride; p.chainOffsets = dChainOffsets; p.chainProgress = dChainProgress;
+            p.chainDone = dChainDone; p.chainTicket = dChainTicket;
+            p.bndInH = p.bndInF = nullptr; p.bndOutH = dChainH; p.bndOutF = dChainF;
+        }
         void* args[] = {&p};
         const int warpsPerBlock = 4 * g.warpsPerPartition;  // one block per SM, k warps per scheduler partition
         const long long warpsNeeded = ((long long)grp.tasks.size() * g.G + 31) / 32;
-        const int blocks = (int)std::max<long long>(1, std::min<long long>(grp.maxBlocks, (warpsNeeded + warpsPerBlock - 1) / warpsPerBlock));
+        int blocks = (int)std::max<long long>(1, std::min<long long>(grp.maxBlocks, (warpsNeeded + warpsPerBlock - 1) / warpsPerBlock));
+        if (g.chain) blocks = g.passes * (int)((grp.tasks.size() + warpsPerBlock - 1) / warpsPerBlock);  // every pass of every quad
         CUDA_TRY(cudaLaunchKernel(fn, dim3(blocks), dim3(32 * warpsPerBlock), args, grp.smemBytes, stream));
         stats_.kernelLaunches++;
     }
@@ -1279,6 +1340,7 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
         auto wanted = [&](const Group& g) {
             const int wpb = 4 * g.g.warpsPerPartition;
             const long long warps = ((long long)g.tasks.size() * g.g.G + 31) / 32;
+            if (g.g.chain) return (int)(g.g.passes * ((warps + wpb - 1) / wpb));  // every pass of every quad has a block
             return (int)std::max<long long>(1, std::min<long long>(g.maxBlocks, (warps + wpb - 1) / wpb));
         };
         std::stable_sort(groups.begin(), groups.end(), [&](const Group& a, const Group& b) { return wanted(a) < wanted(b); });
@@ -1301,7 +1363,7 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
     if (getenv("OPAL_B200_TRACE"))
         for (const Group& g : groups)
             fprintf(stderr, "[opal-b200] group type=%d%s tasks=%zu longest=%d G=%d R=%d k=%d passes=%d blocks<=%d est=%.0f kcycles\n", g.type,
-                    g.g.folded ? " folded" : "", g.tasks.size(),
+                    g.g.folded ? " folded" : g.g.chain ? " chained" : "", g.tasks.size(),
                     g.tasks.empty() ? 0 : lay_->sortedLen[g.type == 0 && !g.g.folded ? 2 * g.tasks[0] : g.tasks[0]], g.g.G, g.g.R,
                     g.g.warpsPerPartition, g.g.passes, g.maxBlocks, g.estCycles / 1e3);
     bool badArgument = false;
@@ -1342,6 +1404,8 @@ int DeviceDb::search(const unsigned char* query, int Q, int Go, int Ge, const in
                      const unsigned char* skip, int* scores, int* endQ, int* endT, float* deviceMs,
                      OpalSearchResult* const* records, bool noAlignmentFill) {
     stats_ = SearchStats();
+    for (void* b : chainScratch_) device_release(device_, b);  // (the previous search has been waited for)
+    chainScratch_.clear();
     // one result of caller index i (end locations already -1 where there is none)
     auto emit = [&](int i, int sc, int eq, int et) {
         if (records) {

@@ -31,10 +31,11 @@ struct Geometry {
     int G = 1, R = 0, tableIndex = 0, passes = 1, Rpad = 0, rowStride = 0, padTop = 0, warpsPerPartition = 4;
     size_t smemBytes = 0;
     bool folded = false;  // one target per warp in both half-words (SearchParams::folded)
+    bool chain = false;   // all passes of a task in one launch, a warp per pass (SearchParams::chain)
 };
 
 struct SearchStats {
-    int kernelLaunches = 0, rerun32 = 0, G = 0, R = 0, passes = 0, warpsPerPartition = 0, groups = 0, foldedTasks = 0;
+    int kernelLaunches = 0, rerun32 = 0, G = 0, R = 0, passes = 0, warpsPerPartition = 0, groups = 0, foldedTasks = 0, chainedTasks = 0;
 };
 
 constexpr int kMaxDevices = 64;  // devices the per-device resource cache is sized for (larger ordinals are rejected)
@@ -176,6 +177,7 @@ private:
     std::vector<cudaStream_t> auxStreams_;
     std::vector<cudaEvent_t> auxEvents_;
     SearchStats stats_;
+    std::vector<void*> chainScratch_;  // device blocks of chained launches (boundary rows, flags), released by the next search
     bool startRecorded_ = false;
     bool keepOnDevice_ = false;   // search_topk: results stay in HBM, the ladder's hand-over list is gathered there
     int* dSelect_ = nullptr;      // search_topk scratch: [count | flagged positions (n) | k records]

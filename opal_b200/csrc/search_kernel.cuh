@@ -108,6 +108,18 @@ struct SearchParams {
     // NW / HW / OV at 16 bits: H of every strip's last row is sampled in every column; a target whose samples leave
     // [rangeLo, rangeHi] is flagged and re-run at 32 bits (see range tracking in the sweep).
     int rangeHi, rangeLo;
+    // Chained passes (the latency class of a query that takes several passes): ALL passes of a task run in one launch,
+    // each on a warp of its own -- block b sweeps pass b % numPasses of the tasks of quad b / numPasses -- and the
+    // boundary row travels from the warp of pass p to the warp of pass p + 1 through HBM / L2 while both are sweeping:
+    // the producer publishes how many columns it has parked (chainProgress), the consumer stays behind that mark.
+    // The longest target of a database then costs its length in steps ONCE instead of once per pass.
+    // bndOutH / bndOutF hold numPasses rows of chainStride entries, chainOffsets[task] is a task's place in a row.
+    int chain;
+    int chainStride;
+    const int* chainOffsets;
+    int* chainProgress;   // [task * numPasses + pass]: columns of that pass's boundary row that are in memory
+    int* chainDone;       // [task * numPasses + pass]: that pass has written its results
+    int* chainTicket;     // blocks take their place in the chain in the order they START (so a producer is never behind its consumer)
 };
 constexpr int kFoldLag = 32;  // columns between the two halves of a folded task = depth of one warp's wavefront
 
@@ -133,6 +145,21 @@ __device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p) {
     uint32_t v;
     asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
+}
+
+// Chained passes: loads that must see what another SM has just written (L1 is not coherent), and the flag accesses.
+__device__ __forceinline__ uint32_t ld_cg_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
 // a * m + b with m a run-time 0 / 1: a select issued as one IMAD on the FMA pipe instead of a compare and a
@@ -281,6 +308,16 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
 
     const int G = p.G, Go = p.gapOpen, Ge = p.gapExt, A = p.A, mode = p.mode;
     const int planeWords = (A + 1) * p.rowStride;
+    // which pass over the query this block sweeps: the launch's (one launch per pass), or -- chained passes -- its own
+    int pass = p.pass, rowBase = p.rowBase, chainQuad = 0;
+    if (p.chain) {
+        __shared__ int ticket;
+        if (threadIdx.x == 0) ticket = atomicAdd(p.chainTicket, 1);
+        __syncthreads();
+        pass = ticket % p.numPasses;
+        chainQuad = ticket / p.numPasses;
+        rowBase = pass * G * R;
+    }
 
     // ---- build the query profile for this pass.  One thread per profile COLUMN (a padded query row of some thread's
     // strip): it reads its query letter once -- the only load with global-memory latency -- and then walks down the
@@ -292,7 +329,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         int q = -1, q2 = -1;  // query letters of the low / high half-word rows; -1 = padding row
         const bool used = t < G && j < R;
         if (used) {
-            const int r = p.rowBase + t * R + j - p.padTop;
+            const int r = rowBase + t * R + j - p.padTop;
             if (r >= 0 && r < p.Q) q = p.query[r];
             q2 = q;
             if (LANES == 2 && p.folded) {  // high half-words: the rows 32 R further down
@@ -355,11 +392,11 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             if (R - j >= 1) P[j] = TR::combine(lds32(plo + 4 * j), LANES == 2 ? lds32(phi + 4 * j) : 0u);
         }
     };
-    const bool firstPass = p.pass == 0, lastPass = p.pass == p.numPasses - 1;
-    const int myRow0 = p.rowBase + t * R - p.padTop;  // query row of this thread's register 0
+    const bool firstPass = pass == 0, lastPass = pass == p.numPasses - 1;
+    const int myRow0 = rowBase + t * R - p.padTop;  // query row of this thread's register 0
     // NW keeps padding at the bottom, so its last query row sits at a run-time position.
     const int lastRowPadded = p.Q - 1 + p.padTop;
-    const int tLast = (lastRowPadded - p.rowBase) / R, jLast = (lastRowPadded - p.rowBase) % R;
+    const int tLast = (lastRowPadded - rowBase) / R, jLast = (lastRowPadded - rowBase) % R;
     // Thread 0 of a group has no thread above it: what enters its strip is row -1 of the matrix (first pass) or
     // the previous pass's boundary row.  notFirst = 0 / 1 blends that in with an IMAD (see blend_fma); the value
     // blended in is kept at 0 in every other thread.
@@ -381,7 +418,10 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         int w = 0;
         if (firstTask) {
             w = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+            if (p.chain) w = chainQuad * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one task per warp: its pass of this quad
             firstTask = false;
+        } else if (p.chain) {
+            break;
         } else {
             if (lane == 0) w = totalWarps + atomicAdd(p.counter, 1);
             w = __shfl_sync(0xffffffffu, w, 0);
@@ -430,6 +470,23 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         const reg* bF = reinterpret_cast<const reg*>(p.bndInF) + off0;
         reg* oH = reinterpret_cast<reg*>(p.bndOutH) + off0;  // ... and of this pass
         reg* oF = reinterpret_cast<reg*>(p.bndOutF) + off0;
+        int* progressOut = nullptr;        // chained passes: this pass's mark, the previous pass's mark and result flag
+        const int* progressIn = nullptr;
+        int avail = 0;                     // columns of the previous pass's row known to be in memory
+        if (p.chain) {
+            const int slot = (taskIdx < p.numTasks ? taskIdx : 0) * p.numPasses + pass;
+            const long long at = (taskIdx < p.numTasks ? p.chainOffsets[taskIdx] : 0);
+            oH = reinterpret_cast<reg*>(p.bndOutH) + (long long)pass * p.chainStride + at;
+            oF = reinterpret_cast<reg*>(p.bndOutF) + (long long)pass * p.chainStride + at;
+            bH = oH - p.chainStride;
+            bF = oF - p.chainStride;
+            progressOut = p.chainProgress + slot;
+            progressIn = progressOut - 1;
+        }
+        // thread 0 of a later pass: wait until the previous pass has parked the columns up to `need` (or all of them)
+        auto await_columns = [&](int need) {
+            while (avail < need && avail < Tmax) avail = ld_acquire(progressIn);
+        };
         // opaque to the compiler: otherwise it re-derives base + (off0 + c) * 4 in every step with seven integer-pipe
         // instructions, stores predicated off or not; as plain pointers the address is one IMAD.WIDE each
         asm volatile("" : "+l"(oH), "+l"(oF));
@@ -449,7 +506,10 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             lcRow[0] = lcRow[1] = -1;
             hiTrack = TR::splat(TR::NEG); loTrack = TR::splat(32767);
             nextBH = synIdle; nextBF = synIdle;
-            if (!firstPass && t == 0 && Tmax > 0) { nextBH = bH[0]; nextBF = bF[0]; }
+            if (!firstPass && t == 0 && Tmax > 0) {
+                if (p.chain) { await_columns(1); nextBH = (reg)ld_cg_u32(bH); nextBF = (reg)ld_cg_u32(bF); }
+                else { nextBH = bH[0]; nextBF = bF[0]; }
+            }
         };
         unsigned storeLimit = (!lastPass && t == G - 1) ? (unsigned)Tmax : 0u;  // columns whose bottom row is parked
         // Rare events of a NW / HW / OV sweep, each at the END of one column of this thread (-2 = never):
@@ -469,7 +529,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             if (!foldedGlobal) {
                 if (t == tLast) { nwCol[0] = T[0] - 1; nwCol[1] = T[1] - 1; }
             } else {  // the last query row sits in the low or in the high half-words
-                const int pos = lastRowPadded - p.rowBase, half = pos >= foldRows ? 1 : 0, posIn = pos - half * foldRows;
+                const int pos = lastRowPadded - rowBase, half = pos >= foldRows ? 1 : 0, posIn = pos - half * foldRows;
                 jLastTask = posIn % R;
                 if (t == posIn / R) nwCol[half] = T[0] - 1 + half * kFoldLag;
             }
@@ -543,7 +603,10 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                     } else {
                         synH = nextBH; synF = nextBF;
                         nextBH = synIdle; nextBF = synIdle;
-                        if (t == 0 && c + 1 < Tmax) { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
+                        if (t == 0 && c + 1 < Tmax) {
+                            if (p.chain) { await_columns(c + 2); nextBH = (reg)ld_cg_u32(bH + c + 1); nextBF = (reg)ld_cg_u32(bF + c + 1); }
+                            else { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
+                        }
                     }
                     upH = TR::blend(upH, notFirst, synH);
                     upF = TR::blend(upF, notFirst, synF);
@@ -686,6 +749,8 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                 if ((unsigned)c < storeLimit) {  // last thread of a group, every pass but the last: park the bottom row
                     asm volatile("st.global.b32 [%0], %1;" :: "l"(oH + c), "r"(outH) : "memory");
                     asm volatile("st.global.b32 [%0], %1;" :: "l"(oF + c), "r"(outF) : "memory");
+                    // chained passes: every 32 columns (and at the end) tell the next pass how far the row has come
+                    if (p.chain && ((c & 31) == 31 || c + 1 == Tmax)) st_release(progressOut, c + 1);
                 }
             }
 
@@ -751,6 +816,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
 #pragma unroll
             for (int l = 0; l < LANES; l++) inexact |= fsc[l] >= p.fastEndLimit;
             if (__any_sync(0xffffffffu, inexact)) {
+                if (p.chain) storeLimit = 0;  // the boundary row is already out (the re-sweep computes the same values)
                 init_state(false);
                 sweep(std::integral_constant<int, kFlavorSWEnd>());
                 reduce(false);
@@ -767,6 +833,10 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             reduce(false);
         }
         const bool pairInexact = false;
+        if (p.chain && !firstPass && t == 0 && taskIdx < p.numTasks) {  // the previous pass's results must be in memory
+            const int* doneIn = p.chainDone + taskIdx * p.numPasses + pass - 1;
+            while (ld_acquire(doneIn) == 0) {}
+        }
 #pragma unroll
         for (int l = 0; l < LANES; l++) {
             if (t == 0 && tgt[l] >= 0) {
@@ -774,10 +844,12 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                 int sc = fsc[l], cc = fcc[l], rr = frr[l];
                 bool overflow = (kSW && sc > p.overflowLimit) || pairInexact || outOfRange[l];
                 if (!firstPass) {
-                    const int ps0 = p.outScore[i];
+                    // (volatile: with chained passes the previous pass wrote these from another SM a moment ago)
+                    const int ps0 = *(volatile int*)(p.outScore + i);
                     if (ps0 == kScoreOverflow) overflow = true;
-                    else if (ps0 != kScoreNone && (sc == kScoreNone || better(ps0, p.outEndT[i], p.outEndQ[i], sc, cc, rr))) {
-                        sc = ps0; cc = p.outEndT[i]; rr = p.outEndQ[i];
+                    else if (ps0 != kScoreNone) {
+                        const int pc = *(volatile int*)(p.outEndT + i), pr = *(volatile int*)(p.outEndQ + i);
+                        if (sc == kScoreNone || better(ps0, pc, pr, sc, cc, rr)) { sc = ps0; cc = pc; rr = pr; }
                     }
                 }
                 if (overflow) sc = kScoreOverflow;
@@ -789,6 +861,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                 }
             }
         }
+        if (p.chain && t == 0 && taskIdx < p.numTasks) st_release(p.chainDone + taskIdx * p.numPasses + pass, 1);
     }
 }
 

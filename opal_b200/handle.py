@@ -54,6 +54,8 @@ class OpalB200(OpalCLibrary):
         L.opalb200_db_last_stats.restype = None
         L.opalb200_db_last_folded.argtypes = [vp]
         L.opalb200_db_last_folded.restype = ci
+        L.opalb200_db_last_chained.argtypes = [vp]
+        L.opalb200_db_last_chained.restype = ci
         L.opalb200_measure_dpx_peak.argtypes = [ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]
         L.opalb200_measure_dpx_peak.restype = ctypes.c_double
         L.opalb200_measure_dpx_peak_mix.argtypes = [ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]
@@ -197,6 +199,7 @@ class ResidentDb:
         self.eng.lib.opalb200_db_last_stats(self.handle, *[ctypes.byref(x) for x in v])
         d = dict(zip(("kernel_launches", "rerun32", "G", "R", "passes", "warps_per_partition", "groups"), (x.value for x in v)))
         d["folded"] = int(self.eng.lib.opalb200_db_last_folded(self.handle))
+        d["chained"] = int(self.eng.lib.opalb200_db_last_chained(self.handle))
         return d
 
     def close(self):
