@@ -311,8 +311,9 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
     // which pass over the query this block sweeps: the launch's (one launch per pass), or -- chained passes -- its own
     int pass = p.pass, rowBase = p.rowBase, chainQuad = 0;
     if (p.chain) {
-        __shared__ int ticket;
-        if (threadIdx.x == 0) ticket = atomicAdd(p.chainTicket, 1);
+        if (threadIdx.x == 0) smem[0] = (uint32_t)atomicAdd(p.chainTicket, 1);  // (the profile is built over it below)
+        __syncthreads();
+        const int ticket = (int)smem[0];
         __syncthreads();
         pass = ticket % p.numPasses;
         chainQuad = ticket / p.numPasses;
