@@ -61,13 +61,13 @@ struct PhaseTrace {
 }  // namespace
 
 // ------------------------------------------------------------------ kernel registry
-#define OPAL_DECLARE_TABLE(R) const void* const* kernel_table_R##R();
+#define OPAL_DECLARE_TABLE(R) const void* const* kernel_table_R##R(); const void* const* kernel_chain_table_R##R();
 OPAL_R_LIST(OPAL_DECLARE_TABLE)
 #undef OPAL_DECLARE_TABLE
 
 const std::vector<KernelTable>& kernel_tables() {
     static const std::vector<KernelTable> tables = {
-#define OPAL_TABLE_ENTRY(R) {R, kernel_table_R##R()},
+#define OPAL_TABLE_ENTRY(R) {R, kernel_table_R##R(), kernel_chain_table_R##R()},
         OPAL_R_LIST(OPAL_TABLE_ENTRY)
 #undef OPAL_TABLE_ENTRY
     };
@@ -1166,7 +1166,7 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
                 const int quads = (int)((m + 3) / 4);
                 for (size_t ti = 0; ti < tables.size(); ti++) {
                     const int R = tables[ti].R;
-                    if (R != 6 && R != 9 && R != 12 && R != 17 && R != 24 && R != 33) continue;
+                    if (!tables[ti].chainFn[0]) continue;  // chained variants exist for a few strip heights (search_kernel.cuh)
                     const int rows = 32 * R, passes = (Q + rows - 1) / rows;
                     if (passes < 2 || passes > 64) continue;
                     if ((long long)passes * rows * 3 > (long long)Q * 4 + 96) continue;  // more than a third padding
@@ -1182,7 +1182,8 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
                     double tB = 0;
                     if (!pick_geometry(Q, A, lanes, tl, m, nT, smemLimit_, numSMs_ - smL, mode, false, flavorClass, &gB, &tB)) continue;
                     const double t = (t_overlapped ? (smL * tL + (numSMs_ - smL) * tB) / numSMs_ : std::max(tL, tB)) + 3000.0;
-                    if (t < bestT * 0.97 || (force && !bestL.chain)) { bestT = t; bestM = m; bestSm = smL; bestL = gL; bestB = gB; }
+                    // (a tenth better at least: a folded or plain latency class of equal speed holds fewer SMs)
+                    if (t < bestT * 0.90 || (force && !bestL.chain)) { bestT = t; bestM = m; bestSm = smL; bestL = gL; bestB = gB; }
                 }
             }
         }
@@ -1251,6 +1252,8 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
     const void* fn = kernel_tables()[g.tableIndex].fn[type * 4 + flavor];
     if (flavor == kFlavorGlobal && 128 * g.warpsPerPartition > launch_bound_for(flavor, g.R))
         fn = kernel_tables()[g.tableIndex].fn[type == 0 ? 8 : type * 4 + flavor];  // Packed16 variant compiled for 384 threads
+    if (g.chain) fn = kernel_tables()[g.tableIndex].chainFn[type * 4 + flavor];
+    if (!fn) { set_error("no kernel for this geometry"); return false; }
     if (!allow_full_smem(device_, fn, smemLimit_)) return false;
     // chained passes: one launch, passes x quads blocks; boundary rows and flags live in a block of their own
     int chainStride = 0;

@@ -24,6 +24,7 @@ constexpr int kFoldTargets = 128, kFoldMinLength = 256;
 struct KernelTable {
     int R;
     const void* const* fn;
+    const void* const* chainFn;  // chained-pass variants [type * 4 + flavor]; entries are null for most strip heights
 };
 const std::vector<KernelTable>& kernel_tables();
 

@@ -20,4 +20,18 @@ static const void* const kTable[9] = {
     (const void*)search_kernel<OPAL_R, kFlavorGlobal, Packed16, 384>,  // three warps per partition (170-register cap)
 };
 const void* const* OPAL_CAT(kernel_table_R, OPAL_R)() { return kTable; }
+
+// chained passes: one warp per scheduler partition (128 threads, no register cap), [type * 4 + flavor]
+#define OPAL_CHAINED(FLAVOR, TYPE) (const void*)search_kernel<OPAL_R, FLAVOR, TYPE, 128, true>
+static const void* const kChainTable[8] = {
+#if OPAL_R == 6 || OPAL_R == 9 || OPAL_R == 12 || OPAL_R == 17 || OPAL_R == 24 || OPAL_R == 33
+    OPAL_CHAINED(kFlavorSWScore, Packed16), OPAL_CHAINED(kFlavorSWEnd, Packed16), OPAL_CHAINED(kFlavorGlobal, Packed16),
+    OPAL_CHAINED(kFlavorSWEndFast, Packed16), OPAL_CHAINED(kFlavorSWScore, Scalar32), OPAL_CHAINED(kFlavorSWEnd, Scalar32),
+    OPAL_CHAINED(kFlavorGlobal, Scalar32), OPAL_CHAINED(kFlavorSWEnd, Scalar32),
+#else
+    nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+#endif
+};
+static_assert(chain_strip_height(OPAL_R) == (OPAL_R == 6 || OPAL_R == 9 || OPAL_R == 12 || OPAL_R == 17 || OPAL_R == 24 || OPAL_R == 33), "keep in step with search_kernel.cuh");
+const void* const* OPAL_CAT(kernel_chain_table_R, OPAL_R)() { return kChainTable; }
 }  // namespace opalb200

@@ -299,7 +299,11 @@ __device__ __forceinline__ bool better(int s, int c, int r, int S, int C, int R)
 // Row 0 is the "no residue" letter, row y+1 is target letter y.  Word (row, t*Rpad + j) of plane LO
 // holds the biased score of padded query row rowBase + t*R + j against that letter in its low
 // half-word (sign bits cleared); plane HI holds it shifted left by 16.
-template <int R, int FLAVOR, class TR, int MAXT = launch_bound_for(FLAVOR, R)>
+// CHAIN: the variant for chained passes (SearchParams::chain), compiled for a few strip heights and for one warp per
+// scheduler partition only; the other instantiations carry none of its code (the pointers and marks it keeps live
+// across the sweep cost the capped 384-thread kernels a fifth of their speed when they were a run-time branch).
+constexpr bool chain_strip_height(int R) { return R == 6 || R == 9 || R == 12 || R == 17 || R == 24 || R == 33; }
+template <int R, int FLAVOR, class TR, int MAXT = launch_bound_for(FLAVOR, R), bool CHAIN = false>
 __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
     typedef typename TR::reg reg;
     constexpr int LANES = TR::LANES;
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
     const int planeWords = (A + 1) * p.rowStride;
     // which pass over the query this block sweeps: the launch's (one launch per pass), or -- chained passes -- its own
     int pass = p.pass, rowBase = p.rowBase, chainQuad = 0;
-    if (p.chain) {
+    if (CHAIN) {
         if (threadIdx.x == 0) smem[0] = (uint32_t)atomicAdd(p.chainTicket, 1);  // (the profile is built over it below)
         __syncthreads();
         const int ticket = (int)smem[0];
@@ -419,9 +423,9 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         int w = 0;
         if (firstTask) {
             w = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
-            if (p.chain) w = chainQuad * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one task per warp: its pass of this quad
+            if (CHAIN) w = chainQuad * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one task per warp: its pass of this quad
             firstTask = false;
-        } else if (p.chain) {
+        } else if (CHAIN) {
             break;
         } else {
             if (lane == 0) w = totalWarps + atomicAdd(p.counter, 1);
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         int* progressOut = nullptr;        // chained passes: this pass's mark, the previous pass's mark and result flag
         const int* progressIn = nullptr;
         int avail = 0;                     // columns of the previous pass's row known to be in memory
-        if (p.chain) {
+        if (CHAIN) {
             const int slot = (taskIdx < p.numTasks ? taskIdx : 0) * p.numPasses + pass;
             const long long at = (taskIdx < p.numTasks ? p.chainOffsets[taskIdx] : 0);
             oH = reinterpret_cast<reg*>(p.bndOutH) + (long long)pass * p.chainStride + at;
@@ -508,7 +512,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             hiTrack = TR::splat(TR::NEG); loTrack = TR::splat(32767);
             nextBH = synIdle; nextBF = synIdle;
             if (!firstPass && t == 0 && Tmax > 0) {
-                if (p.chain) { await_columns(1); nextBH = (reg)ld_cg_u32(bH); nextBF = (reg)ld_cg_u32(bF); }
+                if (CHAIN) { await_columns(1); nextBH = (reg)ld_cg_u32(bH); nextBF = (reg)ld_cg_u32(bF); }
                 else { nextBH = bH[0]; nextBF = bF[0]; }
             }
         };
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                         synH = nextBH; synF = nextBF;
                         nextBH = synIdle; nextBF = synIdle;
                         if (t == 0 && c + 1 < Tmax) {
-                            if (p.chain) { await_columns(c + 2); nextBH = (reg)ld_cg_u32(bH + c + 1); nextBF = (reg)ld_cg_u32(bF + c + 1); }
+                            if (CHAIN) { await_columns(c + 2); nextBH = (reg)ld_cg_u32(bH + c + 1); nextBF = (reg)ld_cg_u32(bF + c + 1); }
                             else { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
                         }
                     }
@@ -751,7 +755,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                     asm volatile("st.global.b32 [%0], %1;" :: "l"(oH + c), "r"(outH) : "memory");
                     asm volatile("st.global.b32 [%0], %1;" :: "l"(oF + c), "r"(outF) : "memory");
                     // chained passes: every 32 columns (and at the end) tell the next pass how far the row has come
-                    if (p.chain && ((c & 31) == 31 || c + 1 == Tmax)) st_release(progressOut, c + 1);
+                    if (CHAIN && ((c & 31) == 31 || c + 1 == Tmax)) st_release(progressOut, c + 1);
                 }
             }
 
@@ -817,7 +821,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
 #pragma unroll
             for (int l = 0; l < LANES; l++) inexact |= fsc[l] >= p.fastEndLimit;
             if (__any_sync(0xffffffffu, inexact)) {
-                if (p.chain) storeLimit = 0;  // the boundary row is already out (the re-sweep computes the same values)
+                if (CHAIN) storeLimit = 0;  // the boundary row is already out (the re-sweep computes the same values)
                 init_state(false);
                 sweep(std::integral_constant<int, kFlavorSWEnd>());
                 reduce(false);
@@ -834,7 +838,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             reduce(false);
         }
         const bool pairInexact = false;
-        if (p.chain && !firstPass && t == 0 && taskIdx < p.numTasks) {  // the previous pass's results must be in memory
+        if (CHAIN && !firstPass && t == 0 && taskIdx < p.numTasks) {  // the previous pass's results must be in memory
             const int* doneIn = p.chainDone + taskIdx * p.numPasses + pass - 1;
             while (ld_acquire(doneIn) == 0) {}
         }
@@ -862,7 +866,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                 }
             }
         }
-        if (p.chain && t == 0 && taskIdx < p.numTasks) st_release(p.chainDone + taskIdx * p.numPasses + pass, 1);
+        if (CHAIN && t == 0 && taskIdx < p.numTasks) st_release(p.chainDone + taskIdx * p.numPasses + pass, 1);
     }
 }
 

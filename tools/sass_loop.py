@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Static instruction mix of the sweep loop(s) of search_kernel, from cuobjdump -sass.
 
-usage: tools/sass_loop.py opal_b200/csrc/build/kernels_R17.o [flavor=3] [arith=Packed16]
+usage: tools/sass_loop.py opal_b200/csrc/build/kernels_R17.o [flavor=3] [arith=Packed16] [chain]
 
 For every innermost loop that holds the DPX recurrence (the wavefront step) prints how many instructions of each
 pipe class the straight-line body holds.  Classes follow the B200 measurements in profiles/README.md:
@@ -35,11 +35,14 @@ def main():
     obj = sys.argv[1]
     flavor = sys.argv[2] if len(sys.argv) > 2 else "3"
     arith = sys.argv[3] if len(sys.argv) > 3 else "Packed16"
+    chained = len(sys.argv) > 4 and sys.argv[4] == "chain"
     sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
     funcs = re.split(r"\n\s*Function : ", sass)
     for f in funcs[1:]:
         name = f.split("\n", 1)[0]
         if f"ELi{flavor}ENS_" not in name or arith not in name:
+            continue
+        if ("ELb1E" in name) != chained:  # the chained-pass variants are listed with a fourth argument "chain"
             continue
         ins = []  # (addr, pred, opcode, text)
         for m in re.finditer(r"/\*([0-9a-f]{4,})\*/\s+(@!?U?P\d\s+)?([A-Za-z0-9_.]+)\s*([^;]*);", f):
