@@ -790,6 +790,11 @@ static __global__ void collect_flagged_kernel(const int* score, int to, int* out
     }
 }
 
+// Boundary rows of a chained launch start out "not written yet" (search_kernel.cuh: kChainEmpty).
+static __global__ void fill_words_kernel(uint32_t* p, size_t n, uint32_t v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 // Zero-length targets (the tail of the length-sorted order) get their defined result without a sweep.
 static __global__ void fill_empty_kernel(int* score, int* endQ, int* endT, int from, int to, int sc, int eq, int et) {
     for (int p = from + blockIdx.x * blockDim.x + threadIdx.x; p < to; p += gridDim.x * blockDim.x) { score[p] = sc; endQ[p] = eq; endT[p] = et; }
@@ -1178,7 +1183,7 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
                     gL.G = 32; gL.R = R; gL.tableIndex = (int)ti; gL.passes = passes; gL.Rpad = Rpad; gL.rowStride = rowStride;
                     gL.smemBytes = smem; gL.warpsPerPartition = 1; gL.padTop = mode == kModeNW ? 0 : passes * rows - Q; gL.chain = true;
                     // every pass trails the one above by about three chunks of 32 columns
-                    const double tL = (tl.len[0] + 31 + 96.0 * (passes - 1)) * step_cycles(flavorClass, 1, R) * 1.03 + 30000.0;
+                    const double tL = (tl.len[0] + 31 + 100.0 * (passes - 1)) * step_cycles(flavorClass, 1, R) * 1.08 + 40000.0;
                     double tB = 0;
                     if (!pick_geometry(Q, A, lanes, tl, m, nT, smemLimit_, numSMs_ - smL, mode, false, flavorClass, &gB, &tB)) continue;
                     const double t = (t_overlapped ? (smL * tL + (numSMs_ - smL) * tB) / numSMs_ : std::max(tL, tB)) + 3000.0;
@@ -1257,7 +1262,7 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
     if (!allow_full_smem(device_, fn, smemLimit_)) return false;
     // chained passes: one launch, passes x quads blocks; boundary rows and flags live in a block of their own
     int chainStride = 0;
-    int *dChainOffsets = nullptr, *dChainProgress = nullptr, *dChainDone = nullptr, *dChainTicket = nullptr;
+    int *dChainOffsets = nullptr, *dChainDone = nullptr, *dChainTicket = nullptr;
     uint32_t *dChainH = nullptr, *dChainF = nullptr;
     if (g.chain) {
         std::vector<int> offsets(grp.tasks.size());
@@ -1267,13 +1272,15 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
         }
         chainStride = (chainStride + 63) / 64 * 64;
         const size_t nT = grp.tasks.size(), flags = nT * (size_t)g.passes;
-        const size_t ints = nT + 2 * flags + 64, words = 2 * (size_t)g.passes * (size_t)chainStride;
+        const size_t ints = nT + flags + 64, words = 2 * (size_t)g.passes * (size_t)chainStride;
         int* block = nullptr;
         if (!device_alloc(device_, (void**)&block, sizeof(int) * (ints + words))) return false;
         chainScratch_.push_back(block);
-        dChainOffsets = block; dChainProgress = block + nT; dChainDone = dChainProgress + flags; dChainTicket = dChainDone + flags;
+        dChainOffsets = block; dChainDone = block + nT; dChainTicket = dChainDone + flags;
         dChainH = reinterpret_cast<uint32_t*>(block + ints); dChainF = dChainH + (size_t)g.passes * chainStride;
         CUDA_TRY(cudaMemsetAsync(block, 0, sizeof(int) * ints, stream));
+        fill_words_kernel<<<std::min<size_t>((words + 1023) / 1024, 4 * (size_t)numSMs_), 256, 0, stream>>>(dChainH, words, type == 0 ? kChainEmpty : kChainEmpty32);
+        CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(dChainOffsets, offsets.data(), sizeof(int) * nT, cudaMemcpyHostToDevice, stream));  // (pageable: staged before the call returns)
         stats_.chainedTasks = (int)nT;
     }
@@ -1308,7 +1315,7 @@ bool DeviceDb::launch_group(const Group& grp, int* taskListDevice, cudaStream_t 
             p.rangeLo = rangeTracking_ ? (int)((mode == kModeNW ? -28000 : -16383) + margin) : INT_MIN;
         }
         if (g.chain) {
-            p.chain = 1; p.chainStride = chainStride; p.chainOffsets = dChainOffsets; p.chainProgress = dChainProgress;
+            p.chain = 1; p.chainStride = chainStride; p.chainOffsets = dChainOffsets;
             p.chainDone = dChainDone; p.chainTicket = dChainTicket;
             p.bndInH = p.bndInF = nullptr; p.bndOutH = dChainH; p.bndOutF = dChainF;
         }

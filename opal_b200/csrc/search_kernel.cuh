@@ -110,17 +110,23 @@ struct SearchParams {
     int rangeHi, rangeLo;
     // Chained passes (the latency class of a query that takes several passes): ALL passes of a task run in one launch,
     // each on a warp of its own -- block b sweeps pass b % numPasses of the tasks of quad b / numPasses -- and the
-    // boundary row travels from the warp of pass p to the warp of pass p + 1 through HBM / L2 while both are sweeping:
-    // the producer publishes how many columns it has parked (chainProgress), the consumer stays behind that mark.
+    // boundary row travels from the warp of pass p to the warp of pass p + 1 through HBM / L2 while both are sweeping.
+    // The rows start out filled with a value no cell can take (kChainEmpty); the consumer reads them 32 columns at a
+    // time, two chunks ahead of its first thread, and waits while a chunk still holds that value -- no fence, no
+    // counter: a 32-bit store is atomic, and the producer writes every entry exactly once.
     // The longest target of a database then costs its length in steps ONCE instead of once per pass.
     // bndOutH / bndOutF hold numPasses rows of chainStride entries, chainOffsets[task] is a task's place in a row.
     int chain;
     int chainStride;
     const int* chainOffsets;
-    int* chainProgress;   // [task * numPasses + pass]: columns of that pass's boundary row that are in memory
     int* chainDone;       // [task * numPasses + pass]: that pass has written its results
     int* chainTicket;     // blocks take their place in the chain in the order they START (so a producer is never behind its consumer)
 };
+// Chained passes: "not written yet" in a boundary row.  Both half-words -32768 (or INT_MIN at 32 bits) lies outside
+// every range the kernels guarantee; a sweep that has already left that range (its target is flagged and re-run at 32
+// bits anyway) could still produce the pattern by accident, so the producer never stores it (it stores the pattern + 1).
+constexpr uint32_t kChainEmpty = 0x80008000u;
+constexpr uint32_t kChainEmpty32 = 0x80000000u;
 constexpr int kFoldLag = 32;  // columns between the two halves of a folded task = depth of one warp's wavefront
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -475,26 +481,34 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         const reg* bF = reinterpret_cast<const reg*>(p.bndInF) + off0;
         reg* oH = reinterpret_cast<reg*>(p.bndOutH) + off0;  // ... and of this pass
         reg* oF = reinterpret_cast<reg*>(p.bndOutF) + off0;
-        int* progressOut = nullptr;        // chained passes: this pass's mark, the previous pass's mark and result flag
-        const int* progressIn = nullptr;
-        int avail = 0;                     // columns of the previous pass's row known to be in memory
-        if (CHAIN) {
-            const int slot = (taskIdx < p.numTasks ? taskIdx : 0) * p.numPasses + pass;
+        if (CHAIN) {  // this pass's row and the previous pass's row of the chained launch
             const long long at = (taskIdx < p.numTasks ? p.chainOffsets[taskIdx] : 0);
             oH = reinterpret_cast<reg*>(p.bndOutH) + (long long)pass * p.chainStride + at;
             oF = reinterpret_cast<reg*>(p.bndOutF) + (long long)pass * p.chainStride + at;
             bH = oH - p.chainStride;
             bF = oF - p.chainStride;
-            progressOut = p.chainProgress + slot;
-            progressIn = progressOut - 1;
         }
-        // thread 0 of a later pass: wait until the previous pass has parked the columns up to `need` (or all of them)
-        auto await_columns = [&](int need) {
-            while (avail < need && avail < Tmax) avail = ld_acquire(progressIn);
-        };
         // opaque to the compiler: otherwise it re-derives base + (off0 + c) * 4 in every step with seven integer-pipe
         // instructions, stores predicated off or not; as plain pointers the address is one IMAD.WIDE each
         asm volatile("" : "+l"(oH), "+l"(oF));
+        // Chained passes, later pass: the previous pass's row arrives 32 columns at a time, lane i holding column
+        // 32 k + i of the chunk in use (cur) and of the next one (nxt); thread 0 -- at column s in step s -- takes
+        // its column by shuffle.  A chunk is complete when none of its entries is kChainEmpty any more.
+        constexpr uint32_t kEmpty = LANES == 2 ? kChainEmpty : kChainEmpty32;
+        const reg idleV = kSW ? negGo : NEGV;   // boundary row beyond the target's end
+        reg curH = idleV, curF = idleV, nxtH = idleV, nxtF = idleV;
+        auto load_boundary_chunk = [&](int k, reg& h, reg& f) {
+            h = idleV; f = idleV;
+            if (32 * k >= Tmax) return;
+            const int col = 32 * k + lane;
+            bool ok;
+            do {
+                if (col < Tmax) { h = (reg)ld_cg_u32(bH + col); f = (reg)ld_cg_u32(bF + col); }
+                ok = col >= Tmax || ((uint32_t)h != kEmpty && (uint32_t)f != kEmpty);
+            } while (!__all_sync(0xffffffffu, ok));
+            if (col >= Tmax) { h = idleV; f = idleV; }
+        };
+        const uint32_t firstThreadOnly = t == 0 ? 0xffffffffu : 0u;
         reg nextBH, nextBF;
         auto init_state = [&](bool keyTracking) {
 #pragma unroll
@@ -511,10 +525,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             lcRow[0] = lcRow[1] = -1;
             hiTrack = TR::splat(TR::NEG); loTrack = TR::splat(32767);
             nextBH = synIdle; nextBF = synIdle;
-            if (!firstPass && t == 0 && Tmax > 0) {
-                if (CHAIN) { await_columns(1); nextBH = (reg)ld_cg_u32(bH); nextBF = (reg)ld_cg_u32(bF); }
-                else { nextBH = bH[0]; nextBF = bF[0]; }
-            }
+            if (!CHAIN && !firstPass && t == 0 && Tmax > 0) { nextBH = bH[0]; nextBF = bF[0]; }
         };
         unsigned storeLimit = (!lastPass && t == G - 1) ? (unsigned)Tmax : 0u;  // columns whose bottom row is parked
         // Rare events of a NW / HW / OV sweep, each at the END of one column of this thread (-2 = never):
@@ -582,6 +593,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             int c = -t;
             Letters wnext = fetch(c);
             reg P[R];
+            if (CHAIN && !firstPass) { load_boundary_chunk(0, curH, curF); load_boundary_chunk(1, nxtH, nxtF); }
             // row -1 of the matrix as seen by thread 0 (reference src/opal.cpp:716-732; all zeros for SW); NW's
             // -Go - c * Ge walks down by Ge per column
             reg synRow = TR::splat(0), synStep = TR::splat(0);
@@ -605,13 +617,19 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                         synH = synRow;
                         synF = synH;  // F entering row 0 = max(-inf - Ge, H[-1][c] - Go)
                         if (!kSW) synRow = TR::add(synRow, synStep);
+                    } else if (CHAIN) {
+                        // thread 0 is at column s: lane s mod 32 of the chunk in use holds it (zero for the other threads,
+                        // whose value comes from the thread above)
+                        synH = (reg)((uint32_t)__shfl_sync(0xffffffffu, curH, s & 31) & firstThreadOnly);
+                        synF = (reg)((uint32_t)__shfl_sync(0xffffffffu, curF, s & 31) & firstThreadOnly);
+                        if ((s & 31) == 31) {  // on to the next chunk; fetch the one after it (two chunks ahead of thread 0)
+                            curH = nxtH; curF = nxtF;
+                            load_boundary_chunk((s >> 5) + 2, nxtH, nxtF);
+                        }
                     } else {
                         synH = nextBH; synF = nextBF;
                         nextBH = synIdle; nextBF = synIdle;
-                        if (t == 0 && c + 1 < Tmax) {
-                            if (CHAIN) { await_columns(c + 2); nextBH = (reg)ld_cg_u32(bH + c + 1); nextBF = (reg)ld_cg_u32(bF + c + 1); }
-                            else { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
-                        }
+                        if (t == 0 && c + 1 < Tmax) { nextBH = bH[c + 1]; nextBF = bF[c + 1]; }
                     }
                     upH = TR::blend(upH, notFirst, synH);
                     upF = TR::blend(upF, notFirst, synF);
@@ -752,10 +770,13 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                     }
                 }
                 if ((unsigned)c < storeLimit) {  // last thread of a group, every pass but the last: park the bottom row
-                    asm volatile("st.global.b32 [%0], %1;" :: "l"(oH + c), "r"(outH) : "memory");
-                    asm volatile("st.global.b32 [%0], %1;" :: "l"(oF + c), "r"(outF) : "memory");
-                    // chained passes: every 32 columns (and at the end) tell the next pass how far the row has come
-                    if (CHAIN && ((c & 31) == 31 || c + 1 == Tmax)) st_release(progressOut, c + 1);
+                    reg sH = outH, sF = outF;
+                    if (CHAIN) {  // never the "not written yet" pattern (see kChainEmpty)
+                        if ((uint32_t)sH == kEmpty) sH = (reg)(kEmpty + 1u);
+                        if ((uint32_t)sF == kEmpty) sF = (reg)(kEmpty + 1u);
+                    }
+                    asm volatile("st.global.b32 [%0], %1;" :: "l"(oH + c), "r"(sH) : "memory");
+                    asm volatile("st.global.b32 [%0], %1;" :: "l"(oF + c), "r"(sF) : "memory");
                 }
             }
 
