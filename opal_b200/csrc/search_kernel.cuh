@@ -34,6 +34,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include <type_traits>
 
@@ -156,8 +157,11 @@ __device__ __forceinline__ uint32_t ldg_u8(const uint8_t* p) {
 // Chained passes: loads that must see what another SM has just written (L1 is not coherent), and the flag accesses.
 __device__ __forceinline__ uint32_t ld_cg_u32(const void* p) {
     uint32_t v;
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_gpu_u32(void* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
@@ -497,14 +501,21 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         constexpr uint32_t kEmpty = LANES == 2 ? kChainEmpty : kChainEmpty32;
         const reg idleV = kSW ? negGo : NEGV;   // boundary row beyond the target's end
         reg curH = idleV, curF = idleV, nxtH = idleV, nxtF = idleV;
+        bool chainBroken = false;  // a wait was given up: the task's results are not to be trusted (flagged for the 32-bit class)
         auto load_boundary_chunk = [&](int k, reg& h, reg& f) {
             h = idleV; f = idleV;
             if (32 * k >= Tmax) return;
             const int col = 32 * k + lane;
             bool ok;
+            unsigned polls = 0;
             do {
                 if (col < Tmax) { h = (reg)ld_cg_u32(bH + col); f = (reg)ld_cg_u32(bF + col); }
                 ok = col >= Tmax || ((uint32_t)h != kEmpty && (uint32_t)f != kEmpty);
+                if (++polls == (1u << 24)) {  // seconds: the producer is gone (must not happen); leave instead of hanging the device
+                    if (lane == 0) printf("opal-b200: chained pass %d of task %d gave up waiting for columns %d.. of %d\n", pass, taskIdx, 32 * k, Tmax);
+                    chainBroken = true;
+                    break;
+                }
             } while (!__all_sync(0xffffffffu, ok));
             if (col >= Tmax) { h = idleV; f = idleV; }
         };
@@ -775,8 +786,13 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                         if ((uint32_t)sH == kEmpty) sH = (reg)(kEmpty + 1u);
                         if ((uint32_t)sF == kEmpty) sF = (reg)(kEmpty + 1u);
                     }
-                    asm volatile("st.global.b32 [%0], %1;" :: "l"(oH + c), "r"(sH) : "memory");
-                    asm volatile("st.global.b32 [%0], %1;" :: "l"(oF + c), "r"(sF) : "memory");
+                    if (CHAIN) {  // read by another SM while this sweep goes on: stores at device scope
+                        st_gpu_u32(oH + c, (uint32_t)sH);
+                        st_gpu_u32(oF + c, (uint32_t)sF);
+                    } else {
+                        asm volatile("st.global.b32 [%0], %1;" :: "l"(oH + c), "r"(sH) : "memory");
+                        asm volatile("st.global.b32 [%0], %1;" :: "l"(oF + c), "r"(sF) : "memory");
+                    }
                 }
             }
 
@@ -861,14 +877,16 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         const bool pairInexact = false;
         if (CHAIN && !firstPass && t == 0 && taskIdx < p.numTasks) {  // the previous pass's results must be in memory
             const int* doneIn = p.chainDone + taskIdx * p.numPasses + pass - 1;
-            while (ld_acquire(doneIn) == 0) {}
+            unsigned polls = 0;
+            while (ld_acquire(doneIn) == 0)
+                if (++polls == (1u << 24)) { chainBroken = true; break; }  // (as above: never hang the device)
         }
 #pragma unroll
         for (int l = 0; l < LANES; l++) {
             if (t == 0 && tgt[l] >= 0) {
                 const int i = tgt[l];
                 int sc = fsc[l], cc = fcc[l], rr = frr[l];
-                bool overflow = (kSW && sc > p.overflowLimit) || pairInexact || outOfRange[l];
+                bool overflow = (kSW && sc > p.overflowLimit) || pairInexact || outOfRange[l] || (CHAIN && chainBroken);
                 if (!firstPass) {
                     // (volatile: with chained passes the previous pass wrote these from another SM a moment ago)
                     const int ps0 = *(volatile int*)(p.outScore + i);
