@@ -379,10 +379,13 @@ def run_b200_arm(args, rank, local_rank, world):
             for st, key in ((OPAL_SEARCH_SCORE_END, "score+end"), (OPAL_SEARCH_SCORE, "score")):
                 row = {}
                 for q in sorted(w.queries, key=len):
-                    rc, _, _, _, ms = handle.search(q, GAP_OPEN, GAP_EXT, mat, A, st, mode)
-                    if rc != 0:
-                        raise SystemExit(f"search failed rc={rc}: {eng.last_error()}")
-                    row[str(len(q))] = round(len(q) * db.total_residues / 1e6 / ms, 1)
+                    best = None
+                    for _ in range(2):  # best of two: the first use of a kernel variant includes loading it
+                        rc, _, _, _, ms = handle.search(q, GAP_OPEN, GAP_EXT, mat, A, st, mode)
+                        if rc != 0:
+                            raise SystemExit(f"search failed rc={rc}: {eng.last_error()}")
+                        best = ms if best is None else min(best, ms)
+                    row[str(len(q))] = round(len(q) * db.total_residues / 1e6 / best, 1)
                 per_query[f"{mode} {key}"] = row
         extras["per_query_gcups_one_gpu"] = {
             "note": "single searches on rank 0's shard, device-timed first launch to last kernel end, GCUPS of one GPU by query length",

@@ -1114,6 +1114,28 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
     double tAll = 0;
     const int flavorClass = mode == kModeSW ? (wantEnd ? 0 : 1) : 2;
     if (!pick_geometry(Q, A, lanes, tl, 0, nT, smemLimit_, numSMs_, mode, false, flavorClass, &gAll, &tAll)) return false;
+    // A class of a handful of tasks (the few targets that need 32 bits from the start, say) whose query takes several
+    // passes: chained passes for all of them, no bulk group.
+    if (nT < 8 && !getenv("OPAL_B200_NO_CHAIN") && !getenv("OPAL_B200_GEOMETRY")) {
+        const auto& tables = kernel_tables();
+        const int planes = lanes == 2 ? 2 : 1, quads = (int)((nT + 3) / 4);
+        for (size_t ti = 0; ti < tables.size(); ti++) {
+            const int R = tables[ti].R;
+            if (!tables[ti].chainFn[0]) continue;
+            const int rows = 32 * R, passes = (Q + rows - 1) / rows;
+            if (passes < 2 || passes > 64 || (long long)passes * rows * 3 > (long long)Q * 4 + 96) continue;
+            const int Rpad = rpad_of(R), rowStride = 32 * Rpad;
+            const size_t smem = (size_t)planes * (A + 1) * rowStride * 4;
+            if (smem > (size_t)smemLimit_ || passes * quads > numSMs_ / 3) continue;
+            const double t = (tl.len[0] + 31 + 100.0 * (passes - 1)) * step_cycles(flavorClass, 1, R) * 1.08 + 40000.0;
+            if (t < tAll * 0.90) {
+                tAll = t;
+                gAll = Geometry();
+                gAll.G = 32; gAll.R = R; gAll.tableIndex = (int)ti; gAll.passes = passes; gAll.Rpad = Rpad; gAll.rowStride = rowStride;
+                gAll.smemBytes = smem; gAll.warpsPerPartition = 1; gAll.padTop = mode == kModeNW ? 0 : passes * rows - Q; gAll.chain = true;
+            }
+        }
+    }
     // candidate splits: the m longest tasks form the latency class on smL SMs
     double bestT = tAll;
     size_t bestM = 0;

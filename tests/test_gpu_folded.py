@@ -14,6 +14,13 @@ from opal_b200 import datasets, matrices
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _no_chained_passes(monkeypatch):
+    """These tests are about the folded sweep: keep the planner from giving the longest targets of a query of several
+    strips chained passes instead (tests/test_gpu_chained.py covers those)."""
+    monkeypatch.setenv("OPAL_B200_NO_CHAIN", "1")
+
+
 def _tailed_db(rng, sm, n_short, n_long, long_lo, long_hi, planted=None, planted_long=None):
     seqs = [datasets.random_residues(int(x), rng, sm) for x in rng.integers(30, 420, n_short)]
     longs = [datasets.random_residues(int(x), rng, sm) for x in rng.integers(long_lo, long_hi, n_long)]
