@@ -387,6 +387,8 @@ int align_database(DeviceDb* ddb, const unsigned char* query, int Q, unsigned ch
                 ALIGN_OK(dalloc(&dOps, (size_t)opsBytes));
                 ALIGN_OK(dalloc(&dBnd, sizeof(int) * (size_t)std::max<long long>(bndInts, 1)));
                 ALIGN_TRY(cudaMemcpyAsync(dTasks, tasks.data(), sizeof(AlignTask) * nt, cudaMemcpyHostToDevice, stream));
+                // an alignment is shorter than its slot: the unused tail travels back with the rest, so it is defined
+                ALIGN_TRY(cudaMemsetAsync(dOps, 0, (size_t)opsBytes, stream));
                 align_dp_kernel<<<nt, 32, matrixInSmem ? A * A * 4 : 0, stream>>>(dTasks, dOuts, ddb->d_residues(), dQuery, dMatrix, A, Go,
                                                                                    Ge, mode, dFlags, dEq, dBnd, matrixInSmem);
                 ALIGN_TRY(cudaGetLastError());

@@ -1087,7 +1087,8 @@ struct DeviceDb::Group {
 // busy long after everything else has finished (the tail bound of pick_geometry) gets a "latency class":
 // its longest tasks run with 32 threads per task and one warp per scheduler partition on SMs of their own,
 // concurrently with the throughput-oriented bulk group on the remaining SMs.
-bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, int mode, int wantEnd, std::vector<Group>* groups) {
+bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, int mode, int wantEnd, std::vector<Group>* groups,
+                          double deadline) {
     if (list.empty()) return true;
     const int lanes = type == 0 ? 2 : 1;
     // Packed16 works on the pairs fixed at packing time (targets 2p, 2p+1): a pair runs if either member
@@ -1114,6 +1115,21 @@ bool DeviceDb::plan_class(int type, const std::vector<int>& list, int Q, int A, 
     double tAll = 0;
     const int flavorClass = mode == kModeSW ? (wantEnd ? 0 : 1) : 2;
     if (!pick_geometry(Q, A, lanes, tl, 0, nT, smemLimit_, numSMs_, mode, false, flavorClass, &gAll, &tAll)) return false;
+    // A small class beside one that takes much longer (the sixteen targets of a global-mode search that need 32 bits
+    // beside half a million that do not): it cannot end the search, so it holds the fewest SMs on which it still ends
+    // well inside the other class's time instead of the many that end it soonest (measured on BASELINE configs[2],
+    // NW, Q = 850: a chained 32-bit class on 12 SMs made the search 6 % slower than a plain one on 4).
+    if (deadline > 0 && nT <= 256 && !getenv("OPAL_B200_GEOMETRY") && !getenv("OPAL_B200_SPLIT") && !getenv("OPAL_B200_CHAIN")) {
+        for (int sms = 1; sms <= 8; sms *= 2) {
+            Geometry g;
+            double t = 0;
+            if (!pick_geometry(Q, A, lanes, tl, 0, nT, smemLimit_, sms, mode, false, flavorClass, &g, &t) || t > 0.6 * deadline) continue;
+            Group grp;
+            grp.type = type; grp.estCycles = t; grp.tasks = tasks; grp.g = g; grp.maxBlocks = sms; grp.smemBytes = g.smemBytes;
+            groups->push_back(std::move(grp));
+            return true;
+        }
+    }
     // A class of a handful of tasks (the few targets that need 32 bits from the start, say) whose query takes several
     // passes: chained passes for all of them, no bulk group.
     if (nT < 8 && !getenv("OPAL_B200_NO_CHAIN") && !getenv("OPAL_B200_GEOMETRY")) {
@@ -1359,8 +1375,18 @@ int DeviceDb::run_classes(const std::vector<std::pair<int, const std::vector<int
                           const int* dMatrix, int Q, int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot) {
     std::vector<Group> groups;
     PhaseTrace trace("run_classes");
-    for (auto& c : classes)
-        if (!plan_class(c.first, *c.second, Q, A, mode, wantEnd, &groups)) return OPAL_B200_ERR_CUDA;
+    // the class with the most targets first: what it is estimated to take is the time the small ones may hide in
+    std::vector<size_t> orderOfClasses(classes.size());
+    for (size_t i = 0; i < classes.size(); i++) orderOfClasses[i] = i;
+    std::stable_sort(orderOfClasses.begin(), orderOfClasses.end(),
+                     [&](size_t a, size_t b) { return classes[a].second->size() > classes[b].second->size(); });
+    double deadline = 0;
+    for (size_t i : orderOfClasses) {
+        const size_t before = groups.size();
+        if (!plan_class(classes[i].first, *classes[i].second, Q, A, mode, wantEnd, &groups, deadline)) return OPAL_B200_ERR_CUDA;
+        if (deadline == 0)
+            for (size_t g = before; g < groups.size(); g++) deadline = std::max(deadline, groups[g].estCycles);
+    }
     if (groups.empty()) return 0;
     trace.mark("plan");
     stats_.groups = (int)groups.size();

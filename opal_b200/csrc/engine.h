@@ -143,7 +143,8 @@ private:
     DeviceDb* clone_context();
     bool alloc_search_buffers();
     struct Group;
-    bool plan_class(int type, const std::vector<int>& list, int Q, int A, int mode, int wantEnd, std::vector<Group>* groups);
+    bool plan_class(int type, const std::vector<int>& list, int Q, int A, int mode, int wantEnd, std::vector<Group>* groups,
+                    double deadline = 0);
     bool launch_group(const Group& grp, int* taskListDevice, cudaStream_t stream, const unsigned char* dQuery, const int* dMatrix,
                       int Q, int Go, int Ge, int A, int wantEnd, int mode, int maxScore, int* launchSlot);
     int run_classes(const std::vector<std::pair<int, const std::vector<int>*>>& classes, const unsigned char* dQuery,

@@ -123,7 +123,10 @@ def test_random_alignments_vs_oracle(product, oracle, mode, seed):
         if oracle_valid:
             assert dg[i] == dw[i], (mode, i, dg[i], dw[i])
             same += 1
-    assert same >= len(db) * (0.95 if mode == "SW" else 0.5)
+    # share of the targets on which the oracle's literal restatement of findAlignment yields a consistent alignment (and
+    # the product's must then be identical): measured on these seeds 60/60 for SW and NW, >= 50/60 for HW, >= 56/60 for OV
+    print(f"{mode} seed {seed}: identical to the oracle on {same} of {len(db)} targets, valid on all")
+    assert same >= len(db) * {"SW": 1.0, "NW": 1.0, "HW": 0.8, "OV": 0.9}[mode]
     free_alignments(got)
     free_alignments(want)
 

@@ -1,6 +1,6 @@
 """Small searches that together touch every kernel path (run under compute-sanitizer by tools/sanitize.sh):
 the README example (all modes, alignments), a folded latency class beside a bulk group, a multi-pass query with
-boundary rows through HBM, a 16 -> 32 bit re-run, a-priori 32-bit routing, the alignment stage, a batch with several
+boundary rows through HBM, chained passes, a 16 -> 32 bit re-run, a-priori 32-bit routing, the alignment stage, a batch with several
 queries in flight, the top-k pipeline and two shards on one device.  Every result is compared with the oracle."""
 import os
 import sys
@@ -51,6 +51,12 @@ for mode in ("SW", "NW", "HW", "OV"):
     same(q300, db, 11, 1, sm.flat(), 23, mode, 1)
 same(datasets.random_residues(1300, rng, sm), SequenceDB.from_sequences(seqs[:40]), 11, 1, sm.flat(), 23, "SW", 1)
 same(datasets.random_residues(1300, rng, sm), SequenceDB.from_sequences(seqs[:40]), 11, 1, sm.flat(), 23, "OV", 1)
+# chained passes (every pass of a long query on a warp of its own, boundary rows handed over through L2)
+os.environ["OPAL_B200_CHAIN"] = "1"
+q1300 = datasets.random_residues(1300, rng, sm)
+for mode in ("SW", "NW", "HW", "OV"):
+    same(q1300, SequenceDB.from_sequences(seqs[:40]), 11, 1, sm.flat(), 23, mode, 1)
+del os.environ["OPAL_B200_CHAIN"]
 # 16 -> 32 bit re-run (8 x BLOSUM62 on near-identical sequences) and a-priori 32-bit routing (huge gap penalties)
 big = (sm.flat() * 40).astype(np.int32)
 qq = datasets.random_residues(400, rng, sm)
