@@ -254,7 +254,10 @@ int opalSearchDatabase(unsigned char query[], int queryLength, unsigned char* db
     // and following them.
     long long total = 0;
     for (int i = 0; i < dbLength && modeOk; i++) total += dbSeqLengths[i] > 0 ? dbSeqLengths[i] : 0;
-    int K = total / std::max(D, 1) >= (96LL << 20) ? 4 : total / std::max(D, 1) >= (32LL << 20) ? 3 : 1;
+    // Measured on BASELINE configs[2] (60 calls, 16 host threads): the whole database on one device (207 M residues) gains
+    // 9 % from four slices; half of it (104 M) is indifferent; a quarter (52 M) LOSES 13 % with three and an eighth 33 %
+    // with two -- every slice is a search of its own (plans, passes, launches), which a short search does not win back.
+    int K = total / std::max(D, 1) >= (144LL << 20) ? 4 : 1;
     if (const char* e = getenv("OPAL_B200_SLICES")) K = std::max(1, std::min(atoi(e), 16));
     K = std::min(K, std::max(dbLength / (2 * std::max(D, 1)), 1));
     if (D * K <= 1 || !modeOk)
