@@ -379,9 +379,13 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
     const int groupInWarp = lane / G;
     const int groupsPerWarp = 32 / G;
     const uint32_t smemBase = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t myLo = smemBase + 4u * (uint32_t)(t * p.Rpad);
-    const uint32_t myHi = myLo + 4u * (uint32_t)planeWords;
-    const uint32_t rowBytes = 4u * (uint32_t)p.rowStride;
+    uint32_t myLo = smemBase + 4u * (uint32_t)(t * p.Rpad);
+    uint32_t myHi = myLo + 4u * (uint32_t)planeWords;
+    uint32_t rowBytes = 4u * (uint32_t)p.rowStride;
+    // opaque to the compiler: it otherwise re-derives them from the CTA id, t and the launch parameters in every step
+    // (six instructions of the sweep loop, measured in the executed SASS of the R = 32 bulk kernel)
+    // (NW / HW / OV only: the SW loops are laid out differently and were measured no shorter with it)
+    if constexpr (!kSW) asm volatile("" : "+r"(myLo), "+r"(myHi), "+r"(rowBytes));
     const reg negGe = TR::splat(-Ge), negGo = TR::splat(-Go), negGmin = TR::splat(-min(Ge, Go));
     const reg NEGV = TR::splat(TR::NEG);
     // (Keeping P[] live across steps and reloading each chunk for the next column right after its use was
@@ -408,6 +412,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         }
     };
     const bool firstPass = pass == 0, lastPass = pass == p.numPasses - 1;
+    const bool firstPassOfLaunch = firstPass;  // (the sweep shadows firstPass with its compile-time copy)
     const int myRow0 = rowBase + t * R - p.padTop;  // query row of this thread's register 0
     // NW keeps padding at the bottom, so its last query row sits at a run-time position.
     const int lastRowPadded = p.Q - 1 + p.padTop;
@@ -562,6 +567,15 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             }
         }
         if (foldedGlobal && mode == kModeOV) ovScanCol = T[0] - 1;
+        // Tall strips (separate compares): the only event INSIDE a sweep is the last column of the shorter member of a pair
+        // of unequal lengths -- OV scans it, NW reads its result cell there.  The longer member's last column (and the
+        // shorter one's when the lengths are equal, the usual case in a sorted database) is still in HG[] when the sweep
+        // ends and is read there.  One column, one compare per step.
+        int evCol = -2;
+        if (!kOneCompare && FLAVOR == kFlavorGlobal && LANES == 2 && T[1] != T[0]) {
+            if (mode == kModeOV) evCol = T[1] - 1;
+            else if (mode == kModeNW && lastPass && t == tLast) evCol = T[1] - 1;
+        }
         const int foldInitCol = foldedGlobal ? kFoldLag - 1 : -2;
         auto next_event = [&](int after) {
             int e = 0x7fffffff;
@@ -573,7 +587,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         };
         int nextEvent = next_event(-1);
         if (kOneCompare) asm volatile("" : "+r"(storeLimit), "+r"(nextEvent));
-        else asm volatile("" : "+r"(storeLimit), "+r"(ovScanCol), "+r"(nwCol[0]), "+r"(nwCol[1]));
+        else asm volatile("" : "+r"(storeLimit), "+r"(evCol));
 
         // OV: best cell of the last target column among this thread's rows (first row on ties), half-word l
         auto scan_last_column = [&](int l) {
@@ -599,8 +613,13 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         };
         // One sweep of the task with tracking flavor TRACK (kFlavorSWEndFast tasks whose score leaves the exact
         // range of the key are swept a second time with kFlavorSWEnd, see below).
-        auto sweep = [&](auto trackTag) {
+        auto sweep_pass = [&](auto trackTag, auto firstTag) {
             constexpr int TRACK = decltype(trackTag)::value;
+            // first pass or a later one, as a compile-time property of the loop: what enters thread 0's strip is produced
+            // in different ways, and selecting between them inside the step costs a compare, a branch and four moves
+            // (NW / HW / OV; the SW flavors keep the run-time test: firstTag = 2)
+            constexpr int kFirst = decltype(firstTag)::value;
+            const bool firstPass = kFirst == 2 ? firstPassOfLaunch : kFirst == 1;
             int c = -t;
             Letters wnext = fetch(c);
             reg P[R];
@@ -612,6 +631,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                 synRow = (reg)((uint32_t)negGo & synMask);  // H = 0 in row -1 (SW, HW, OV)
                 if (!kSW && mode == kModeNW) { synRow = (reg)((uint32_t)TR::splat(-Go - Go) & synMask); synStep = (reg)((uint32_t)negGe & synMask); }
             }
+            if constexpr (!kSW) asm volatile("" : "+r"(synStep));  // (a register, not eight instructions per step re-deriving it from t, mode and folded)
 
 #ifdef OPAL_UNROLL2
 #pragma unroll 2
@@ -727,18 +747,16 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                         if (LANES == 2 && !ph) colHi = c;
                     };
                     if constexpr (!kOneCompare) {
-                        if (mode == kModeNW) {
+                        track_last_row();  // (NW never reads it; testing the mode here would cost more than the three instructions)
+                        if (c == evCol) {  // rare: last column of the shorter member of an unequal pair
+                            if (mode == kModeNW) {
+                                reg v = HG[0];
     #pragma unroll
-                            for (int l = 0; l < LANES; l++)
-                                if (c == nwCol[l]) {
-                                    reg v = HG[0];
-    #pragma unroll
-                                    for (int j = 1; j < R; j++) if (j == jLast) v = HG[j];
-                                    nwScore[l] = TR::lane(v, l) + Go;
-                                }
-                        } else {
-                            track_last_row();
-                            if (c == ovScanCol) scan_last_column(1);
+                                for (int j = 1; j < R; j++) if (j == jLast) v = HG[j];
+                                nwScore[1] = TR::lane(v, 1) + Go;
+                            } else {
+                                scan_last_column(1);
+                            }
                         }
                     } else {
                     if (mode != kModeNW) track_last_row();
@@ -796,6 +814,11 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                 }
             }
 
+        };
+        auto sweep = [&](auto trackTag) {
+            if constexpr (kSW) sweep_pass(trackTag, std::integral_constant<int, 2>());
+            else if (firstPass) sweep_pass(trackTag, std::integral_constant<int, 1>());
+            else sweep_pass(trackTag, std::integral_constant<int, 0>());
         };
 
         // ---- reduce the group's candidates (key: score desc, target index asc, query index asc)
@@ -866,6 +889,14 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
         } else {
             init_state(false);
             sweep(std::integral_constant<int, FLAVOR>());
+            if (FLAVOR == kFlavorGlobal && !kOneCompare && mode == kModeNW && lastPass && t == tLast && T[0] > 0) {
+                // tall strips: the result cell of the longer member (of both when the lengths are equal) is read here
+                reg v = HG[0];
+#pragma unroll
+                for (int j = 1; j < R; j++) if (j == jLast) v = HG[j];
+                nwScore[0] = TR::lane(v, 0) + Go;
+                if (LANES == 2 && T[1] == T[0]) nwScore[1] = TR::lane(v, 1) + Go;
+            }
             if (FLAVOR == kFlavorGlobal && mode == kModeOV) {
                 // threads stop updating their rows after the last column of the longer member: it is still in HG[]
                 // (folded: only the high half-words; the low ones were scanned inside the sweep)
