@@ -385,7 +385,9 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
     // opaque to the compiler: it otherwise re-derives them from the CTA id, t and the launch parameters in every step
     // (six instructions of the sweep loop, measured in the executed SASS of the R = 32 bulk kernel)
     // (NW / HW / OV only: the SW loops are laid out differently and were measured no shorter with it)
-    if constexpr (!kSW) asm volatile("" : "+r"(myLo), "+r"(myHi), "+r"(rowBytes));
+    // (and only the tall strips: at R = 18 the pinned form measured 4.6 % slower, 4920 against 5160 GCUPS at Q = 144)
+    constexpr bool kTightStep = !kSW && !single_event_compare(R);
+    if constexpr (kTightStep) asm volatile("" : "+r"(myLo), "+r"(myHi), "+r"(rowBytes));
     const reg negGe = TR::splat(-Ge), negGo = TR::splat(-Go), negGmin = TR::splat(-min(Ge, Go));
     const reg NEGV = TR::splat(TR::NEG);
     // (Keeping P[] live across steps and reloading each chunk for the next column right after its use was
@@ -617,7 +619,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
             constexpr int TRACK = decltype(trackTag)::value;
             // first pass or a later one, as a compile-time property of the loop: what enters thread 0's strip is produced
             // in different ways, and selecting between them inside the step costs a compare, a branch and four moves
-            // (NW / HW / OV; the SW flavors keep the run-time test: firstTag = 2)
+            // (NW / HW / OV at the tall strips; the other kernels keep the run-time test: firstTag = 2)
             constexpr int kFirst = decltype(firstTag)::value;
             const bool firstPass = kFirst == 2 ? firstPassOfLaunch : kFirst == 1;
             int c = -t;
@@ -631,7 +633,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
                 synRow = (reg)((uint32_t)negGo & synMask);  // H = 0 in row -1 (SW, HW, OV)
                 if (!kSW && mode == kModeNW) { synRow = (reg)((uint32_t)TR::splat(-Go - Go) & synMask); synStep = (reg)((uint32_t)negGe & synMask); }
             }
-            if constexpr (!kSW) asm volatile("" : "+r"(synStep));  // (a register, not eight instructions per step re-deriving it from t, mode and folded)
+            if constexpr (kTightStep) asm volatile("" : "+r"(synStep));  // (a register, not eight instructions per step re-deriving it from t, mode and folded)
 
 #ifdef OPAL_UNROLL2
 #pragma unroll 2
@@ -816,7 +818,7 @@ __global__ void __launch_bounds__(MAXT, 1) search_kernel(const SearchParams p) {
 
         };
         auto sweep = [&](auto trackTag) {
-            if constexpr (kSW) sweep_pass(trackTag, std::integral_constant<int, 2>());
+            if constexpr (!kTightStep) sweep_pass(trackTag, std::integral_constant<int, 2>());
             else if (firstPass) sweep_pass(trackTag, std::integral_constant<int, 1>());
             else sweep_pass(trackTag, std::integral_constant<int, 0>());
         };
