@@ -62,3 +62,22 @@ def test_hot_flavors_do_not_spill():
                 assert stores == 0 and loads == 0, (log, name, stores, loads)
             else:
                 assert stores <= 64, (log, name, stores)
+
+
+def test_tall_global_strips_keep_their_loop_invariants_in_registers():
+    """tools/sass_hot_path.py on the NW / HW / OV bulk kernel at R = 32 (three warps per partition): the hot path of a
+    wavefront step holds the 128 VIADDMNMX of 32 rows, no re-derivation of the profile base address from the CTA id
+    (S2UR) or of loop invariants (LEA / LOP3), and at most 258 instructions (267 before the step was tightened;
+    DESIGN.md section 3, profiles/README.md)."""
+    obj = os.path.join(BUILD, "kernels_R32.o")
+    if obj not in _objects():
+        pytest.skip("R = 32 not built")
+    out = subprocess.run(["python", os.path.join(ROOT, "tools", "sass_hot_path.py"), obj, "2", "Packed16", "384"], capture_output=True,
+                         text=True, check=True).stdout
+    loops = re.findall(r"hot path (\d+): ALU=(\d+).*\n\s+(.*)", out)
+    # (the tool also lists the task loop around them, which holds the epilogue and several hundred instructions more)
+    sweeps = [(int(n), int(alu), ops) for n, alu, ops in loops if "VIADDMNMX=128" in ops and int(n) < 320]
+    assert len(sweeps) == 2, out  # first pass and later passes, as two loops
+    for n, alu, ops in sweeps:
+        assert n <= 258 and alu <= 141, out
+        assert "S2UR" not in ops and "LEA" not in ops and "LOP3" not in ops, out
